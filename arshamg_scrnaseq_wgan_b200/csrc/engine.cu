@@ -1,0 +1,894 @@
+// Host engine + C ABI (include/wgan_b200.h) of the B200-native WGAN(-GP) hot path.
+// One handle per GPU owns: flat parameter / gradient / Adam-m / Adam-v arenas per network (TF
+// variable order [W:140-142]), the activation workspace, and the split-K workspace.  Every step
+// is a fixed sequence of asynchronous launches on the caller's stream (CUDA-graph capturable:
+// no host state changes per step; Adam's beta powers live on the device).
+//
+// Row layout of the critic-step activation buffers (Bl = local rows):
+//     [ fake (x~ = G(z)) | interpolate (x^, later gx)  -- only if lambda_gp != 0 | real (x) ]
+// so that the wgrad products over the stacked rows are single GEMMs with K = 2..3 Bl.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/wgan_b200.h"
+#include "gemm_sm100.cuh"
+#include "kernels.cuh"
+
+using namespace wg;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+inline int round4(int x) { return (x + 3) & ~3; }
+inline size_t round64(size_t x) { return (x + 63) & ~static_cast<size_t>(63); }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+struct TensorDesc {
+  const char* name;
+  int net, rows, cols, ld;
+  size_t offset;
+};
+
+struct Part {          // one product of a split-K accumulated GEMM
+  const float* A;
+  int lda;
+  const float* B;
+  int ldb;
+  int K;
+};
+
+}  // namespace
+
+struct wgan_handle {
+  wgan_config cfg;
+  int Z, Hg, G, Hd, R;
+  int Zl, Hgl, Gl, Hdl;             // padded leading dimensions
+  int num_sms;
+  EncodeTiledFn encode;
+  std::string err;
+  int64_t launches;
+
+  TensorDesc td[12];
+  size_t arena_n[2];                 // floats per net arena (incl. 4-float scalar tail)
+  float* arena[2][4];                // [net][kind]
+  float* powers[2];                  // device {beta1_power, beta2_power} per optimizer
+
+  // workspace
+  float *zbuf, *gh1, *gh2, *xcat, *h1, *h2, *d2, *d1, *dout, *v2, *gd2, *gd1, *dz;
+  float *nsq, *crow, *pen, *norms, *colpart, *splitws, *sample_tmp;
+  size_t splitws_n;
+  int nsq_tiles_max;
+  int last_gx_rows;
+
+  float* P(int t) { return arena[td[t].net][WGAN_KIND_PARAM] + td[t].offset; }
+  float* Gr(int t) { return arena[td[t].net][WGAN_KIND_GRAD] + td[t].offset; }
+  float* scalars(int net) { return arena[net][WGAN_KIND_GRAD] + arena_n[net] - 4; }
+};
+
+namespace {
+
+enum { T_WG1 = 0, T_BG1, T_WG2, T_BG2, T_WG3, T_BG3, T_W1, T_B1, T_W2, T_B2, T_W3, T_B3 };
+
+#define CK(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      char buf_[512];                                                                            \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),        \
+               __FILE__, __LINE__);                                                              \
+      h->err = buf_;                                                                             \
+      return -1;                                                                                 \
+    }                                                                                            \
+  } while (0)
+
+#define FAIL(...)                                  \
+  do {                                             \
+    char buf_[512];                                \
+    snprintf(buf_, sizeof buf_, __VA_ARGS__);      \
+    h->err = buf_;                                 \
+    return -2;                                     \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int r_ = (expr);         \
+    if (r_ != 0) return r_;  \
+  } while (0)
+
+inline int ew_grid(size_t n, int block, int sms) {
+  size_t g = (n + block - 1) / block;
+  size_t cap = static_cast<size_t>(sms) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+int post_launch(wgan_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    h->err = buf;
+    return -3;
+  }
+  h->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor maps
+// ------------------------------------------------------------------------------------------
+int make_map_2d(wgan_handle* h, CUtensorMap* m, const float* ptr, uint64_t inner, uint64_t outer,
+                uint64_t ld_floats, uint32_t box_inner, uint32_t box_outer, bool tf32) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld_floats & 3) != 0)
+    FAIL("TMA operand must be 16-byte aligned with ld %% 4 == 0 (ptr=%p ld=%llu)", (const void*)ptr,
+         (unsigned long long)ld_floats);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_floats * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                         const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(2d) failed with %d", (int)r);
+  return 0;
+}
+
+int make_map_out(wgan_handle* h, CUtensorMap* m, float* ptr, uint64_t N, uint64_t M, uint64_t S,
+                 uint64_t ld_floats, uint64_t slab_floats) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld_floats & 3) != 0 || (slab_floats & 3) != 0)
+    FAIL("TMA output must be 16-byte aligned with ld %% 4 == 0 (ptr=%p ld=%llu)", (void*)ptr,
+         (unsigned long long)ld_floats);
+  cuuint64_t dims[3] = {N, M, S};
+  cuuint64_t strides[2] = {ld_floats * 4, (S > 1 ? slab_floats : ld_floats * M) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(3d out) failed with %d", (int)r);
+  return 0;
+}
+
+int pick_bn(int N) {
+  int best = 256, best_pad = 1 << 30;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    int pad = cdiv(N, bn) * bn;
+    if (pad < best_pad) { best_pad = pad; best = bn; }
+  }
+  return best;
+}
+
+size_t gemm_smem_bytes(int bn, int* stages_out) {
+  const size_t budget = 232448;                       // 227 KB opt-in maximum per CTA
+  const size_t fixed = 1024 + EPI_BUFS * EPI_BOX_BYTES + 256;
+  const size_t stage = BM * 128 + static_cast<size_t>(bn) * 128;
+  int stages = static_cast<int>((budget - fixed) / stage);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  *stages_out = stages;
+  size_t need = fixed + stages * stage;
+  if (need < 120 * 1024) need = 120 * 1024;           // force 1 CTA/SM: each CTA allocates all of TMEM
+  return need;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int grid, cudaStream_t s) {
+  static bool attr_set[16] = {};
+  int dev = h->cfg.device & 15;
+  if (!attr_set[dev]) {
+    CK(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            232448));
+    attr_set[dev] = true;
+  }
+  gemm_tf32_kernel<A_MN, B_MN><<<grid, GEMM_THREADS, smem, s>>>(p);
+  return post_launch(h, "gemm_tf32_kernel");
+}
+
+// D[M,N] = epi( sum_parts A_i * B_i ).  a_mn/b_mn: operand majors (see gemm_sm100.cuh).
+int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts, float* D, int ldd,
+             int M, int N, const EpiParams& epi, int* sumsq_tiles, int force_splits, cudaStream_t s) {
+  if (M <= 0 || N <= 0) FAIL("gemm: empty output %dx%d", M, N);
+  for (int i = 0; i < nparts; ++i)
+    if (parts[i].K <= 0) FAIL("gemm: empty K");
+  const size_t slab = round64(static_cast<size_t>(M) * ldd);
+
+  if (h->cfg.gemm_mode == 1) {
+    // FP32 CUDA-core verification path: raw products into slabs, then the shared finish kernel.
+    float* raw = (nparts == 1) ? D : h->splitws;
+    if (nparts > 1 && slab * nparts > h->splitws_n) FAIL("gemm: split workspace too small");
+    for (int i = 0; i < nparts; ++i) {
+      const Part& pt = parts[i];
+      dim3 grid(cdiv(N, 64), cdiv(M, 64));
+      gemm_fp32_kernel<<<grid, 256, 0, s>>>(pt.A, a_mn ? 1 : pt.lda, a_mn ? pt.lda : 1, pt.B,
+                                            b_mn ? 1 : pt.ldb, b_mn ? pt.ldb : 1,
+                                            raw + (nparts == 1 ? 0 : slab * i), ldd, M, N, pt.K);
+      TRY(post_launch(h, "gemm_fp32_kernel"));
+    }
+    finish_splitk_kernel<<<ew_grid(static_cast<size_t>(M) * 32, 256, h->num_sms), 256, 0, s>>>(
+        raw, slab, nparts, D, ldd, M, N, epi);
+    TRY(post_launch(h, "finish_splitk_kernel"));
+    if (sumsq_tiles) *sumsq_tiles = 1;
+    return 0;
+  }
+
+  const int bn = pick_bn(N);
+  const int m_tiles = cdiv(M, BM), n_tiles = cdiv(N, bn);
+  const int tiles = m_tiles * n_tiles;
+  int stages;
+  const size_t smem = gemm_smem_bytes(bn, &stages);
+
+  // split-K policy: fill ~2 waves when the output has few tiles, at least 8 k-blocks per split
+  int splits[2], kbps[2], total_splits = 0;
+  for (int i = 0; i < nparts; ++i) {
+    const int total_kb = cdiv(parts[i].K, BK);
+    int sp = 1;
+    if (force_splits > 0) {
+      sp = force_splits;
+    } else if (tiles * nparts < h->num_sms) {
+      sp = cdiv(2 * h->num_sms, tiles * nparts);
+      if (sp > total_kb / 8) sp = total_kb / 8;
+    }
+    if (sp > total_kb) sp = total_kb;
+    if (sp < 1) sp = 1;
+    int per = cdiv(total_kb, sp);
+    sp = cdiv(total_kb, per);                         // no empty split
+    splits[i] = sp;
+    kbps[i] = per;
+    total_splits += sp;
+  }
+  if (total_splits > 1 && slab * total_splits > h->splitws_n) {
+    if (nparts > 1) FAIL("gemm: split workspace too small for %d slabs of %zu floats", total_splits, slab);
+    splits[0] = 1;
+    kbps[0] = cdiv(parts[0].K, BK);
+    total_splits = 1;
+  }
+  const bool direct = (total_splits == 1);
+  float* out = direct ? D : h->splitws;
+
+  int slab0 = 0;
+  for (int i = 0; i < nparts; ++i) {
+    const Part& pt = parts[i];
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, BM, true));
+    else       TRY(make_map_2d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, 32, 32, true));
+    if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, bn, true));
+    else       TRY(make_map_2d(h, &p.tma_b, pt.B, N, pt.K, pt.ldb, 32, 32, true));
+    TRY(make_map_out(h, &p.tma_d, out + (direct ? 0 : slab * slab0), N, M, splits[i], ldd, slab));
+    p.M = M; p.N = N; p.K = pt.K;
+    p.bn = bn;
+    p.splits = direct ? 1 : splits[i];
+    p.kb_per_split = kbps[i];
+    p.m_tiles = m_tiles; p.n_tiles = n_tiles;
+    p.stages = stages;
+    p.total_kb = cdiv(pt.K, BK);
+    if (direct) p.epi = epi;
+    else { p.epi.act = 0; p.splits = splits[i]; }
+    // when the partials go to the workspace the fused epilogue must stay off even for 1 split
+    const bool raw_single = (!direct && splits[i] == 1);
+    if (raw_single) { memset(&p.epi, 0, sizeof p.epi); }
+    int grid = tiles * splits[i];
+    if (grid > h->num_sms) grid = h->num_sms;
+    if (!a_mn && b_mn) TRY((launch_tc<false, true>(h, p, smem, grid, s)));
+    else if (!a_mn && !b_mn) TRY((launch_tc<false, false>(h, p, smem, grid, s)));
+    else if (a_mn && b_mn) TRY((launch_tc<true, true>(h, p, smem, grid, s)));
+    else FAIL("gemm: A MN-major with B K-major is not instantiated");
+    slab0 += splits[i];
+  }
+  if (!direct) {
+    finish_splitk_kernel<<<ew_grid(static_cast<size_t>(M) * 32, 256, h->num_sms), 256, 0, s>>>(
+        h->splitws, slab, total_splits, D, ldd, M, N, epi);
+    TRY(post_launch(h, "finish_splitk_kernel"));
+    if (sumsq_tiles) *sumsq_tiles = 1;
+  } else if (sumsq_tiles) {
+    *sumsq_tiles = n_tiles;
+  }
+  return 0;
+}
+
+inline EpiParams epi_none() {
+  EpiParams e;
+  memset(&e, 0, sizeof e);
+  return e;
+}
+inline EpiParams epi_bias_lrelu(const float* bias, float alpha) {
+  EpiParams e = epi_none();
+  e.bias = bias; e.act = 1; e.alpha = alpha;
+  return e;
+}
+inline EpiParams epi_mask(const float* aux, int ld_aux, float alpha) {
+  EpiParams e = epi_none();
+  e.aux = aux; e.ld_aux = ld_aux; e.alpha = alpha;
+  return e;
+}
+
+int gemm1(wgan_handle* h, bool a_mn, bool b_mn, const float* A, int lda, const float* B, int ldb,
+          float* D, int ldd, int M, int N, int K, const EpiParams& e, cudaStream_t s,
+          int* sumsq_tiles = nullptr) {
+  Part p{A, lda, B, ldb, K};
+  return run_gemm(h, a_mn, b_mn, &p, 1, D, ldd, M, N, e, sumsq_tiles, 0, s);
+}
+
+int colsum(wgan_handle* h, const ColsumSeg* segs, int nseg, int N, float* out, cudaStream_t s) {
+  ColsumArgs a;
+  memset(&a, 0, sizeof a);
+  int maxrows = 1;
+  for (int i = 0; i < nseg; ++i) { a.seg[i] = segs[i]; if (segs[i].rows > maxrows) maxrows = segs[i].rows; }
+  a.nseg = nseg; a.N = N;
+  int RC = cdiv(maxrows, 64);
+  if (RC > 64) RC = 64;
+  if (RC < 1) RC = 1;
+  dim3 grid(cdiv(N, 32), RC);
+  colsum_partial_kernel<<<grid, 256, 0, s>>>(a, h->colpart);
+  TRY(post_launch(h, "colsum_partial_kernel"));
+  colsum_final_kernel<<<cdiv(N, 256), 256, 0, s>>>(h->colpart, RC, N, out);
+  return post_launch(h, "colsum_final_kernel");
+}
+
+// Bring a caller matrix into a TMA-legal layout (16 B aligned, ld % 4 == 0); copies only if needed.
+int stage_input(wgan_handle* h, const float* src, int ld, int rows, int cols, float* staging,
+                int ld_staging, const float** out_ptr, int* out_ld, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (ld & 3) == 0) {
+    *out_ptr = src; *out_ld = ld;
+    return 0;
+  }
+  CK(cudaMemcpy2DAsync(staging, static_cast<size_t>(ld_staging) * 4, src, static_cast<size_t>(ld) * 4,
+                       static_cast<size_t>(cols) * 4, rows, cudaMemcpyDeviceToDevice, s));
+  *out_ptr = staging; *out_ld = ld_staging;
+  return 0;
+}
+
+// Generator forward [W:61-83]: gh1, gh2 and x~ (into `xt`, ld `ldxt`).
+int generator_forward(wgan_handle* h, const float* z, int ldz, int rows, float* xt, int ldxt,
+                      cudaStream_t s) {
+  const float a = h->cfg.alpha;
+  TRY(gemm1(h, false, true, z, ldz, h->P(T_WG1), h->td[T_WG1].ld, h->gh1, h->Hgl, rows, h->Hg, h->Z,
+            epi_bias_lrelu(h->P(T_BG1), a), s));
+  TRY(gemm1(h, false, true, h->gh1, h->Hgl, h->P(T_WG2), h->td[T_WG2].ld, h->gh2, h->Hgl, rows, h->Hg,
+            h->Hg, epi_bias_lrelu(h->P(T_BG2), a), s));
+  TRY(gemm1(h, false, true, h->gh2, h->Hgl, h->P(T_WG3), h->td[T_WG3].ld, xt, ldxt, rows, h->G, h->Hg,
+            epi_bias_lrelu(h->P(T_BG3), a), s));
+  return 0;
+}
+
+int check_rows(wgan_handle* h, int rows, int global_batch) {
+  if (rows <= 0 || rows > h->R) FAIL("rows=%d outside (0, max_batch=%d]", rows, h->R);
+  if (global_batch < rows) FAIL("global_batch=%d < rows=%d", global_batch, rows);
+  return 0;
+}
+
+int adam_apply(wgan_handle* h, int net, cudaStream_t s) {
+  const size_t n4 = (h->arena_n[net] - 4) / 4;     // scalar tail excluded
+  adam_kernel<<<ew_grid(n4, 256, h->num_sms), 256, 0, s>>>(
+      h->arena[net][WGAN_KIND_PARAM], h->arena[net][WGAN_KIND_GRAD], h->arena[net][WGAN_KIND_M],
+      h->arena[net][WGAN_KIND_V], n4, h->powers[net], h->cfg.learn_rate, h->cfg.beta1, h->cfg.beta2,
+      h->cfg.epsilon);
+  TRY(post_launch(h, "adam_kernel"));
+  adam_finish_kernel<<<1, 32, 0, s>>>(h->powers[net], h->cfg.beta1, h->cfg.beta2);
+  return post_launch(h, "adam_finish_kernel");
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int wgan_padded_ld(int cols) { return cols == 1 ? 1 : round4(cols); }
+int wgan_tensor_count(void) { return 12; }
+
+const char* wgan_last_error(const wgan_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int64_t wgan_launch_count(const wgan_handle* h) { return h ? h->launches : 0; }
+
+void wgan_destroy(wgan_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (int n = 0; n < 2; ++n) {
+    for (int k = 0; k < 4; ++k) cudaFree(h->arena[n][k]);
+    cudaFree(h->powers[n]);
+  }
+  float* bufs[] = {h->zbuf, h->gh1, h->gh2, h->xcat, h->h1, h->h2, h->d2, h->d1, h->dout, h->v2, h->gd2,
+                   h->gd1, h->dz, h->nsq, h->crow, h->pen, h->norms, h->colpart, h->splitws, h->sample_tmp};
+  for (float* b : bufs) cudaFree(b);
+  delete h;
+}
+
+int wgan_create(const wgan_config* cfg, wgan_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return -2; }
+  *out = nullptr;
+  wgan_handle* h = new wgan_handle();
+  h->cfg = *cfg;
+  h->launches = 0;
+  h->last_gx_rows = 0;
+  for (int n = 0; n < 2; ++n) { for (int k = 0; k < 4; ++k) h->arena[n][k] = nullptr; h->powers[n] = nullptr; }
+  h->zbuf = h->gh1 = h->gh2 = h->xcat = h->h1 = h->h2 = h->d2 = h->d1 = h->dout = h->v2 = h->gd2 = h->gd1 =
+      h->dz = h->nsq = h->crow = h->pen = h->norms = h->colpart = h->splitws = h->sample_tmp = nullptr;
+  auto fail = [&](const std::string& m) { g_create_error = m; wgan_destroy(h); return -1; };
+
+  h->Z = cfg->noise_input_size; h->Hg = cfg->inflate_to_size; h->G = cfg->gex_size;
+  h->Hd = cfg->disc_internal_size; h->R = cfg->max_batch;
+  if (h->Z <= 0 || h->Hg <= 0 || h->G <= 0 || h->Hd <= 0 || h->R <= 0) return fail("non-positive dimension in config");
+  if (cfg->gemm_mode != 0 && cfg->gemm_mode != 1) return fail("gemm_mode must be 0 (TF32 tcgen05) or 1 (FP32 verify)");
+  h->Zl = round4(h->Z); h->Hgl = round4(h->Hg); h->Gl = round4(h->G); h->Hdl = round4(h->Hd);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail("no CUDA device: this library has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("device ordinal out of range");
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail("cudaSetDevice failed");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail("this library is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  h->num_sms = prop.multiProcessorCount;
+
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+    return fail("cuTensorMapEncodeTiled entry point not available");
+  h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+
+  if (cudaMemcpyToSymbol(c_poisson1_cdf, nullptr, 0) != cudaSuccess) { /* symbol touch; real upload below */ }
+  {
+    float cdf[12];
+    double acc = 0.0, term = exp(-1.0);
+    for (int k = 0; k < 12; ++k) {
+      if (k > 0) term /= k;
+      acc += term;
+      cdf[k] = static_cast<float>(acc);
+    }
+    if (cudaMemcpyToSymbol(c_poisson1_cdf, cdf, sizeof cdf) != cudaSuccess) return fail("constant upload failed");
+  }
+
+  // ---- arenas in TF variable creation order [W:128-130,140-142] ----
+  static const char* names[12] = {
+      "generator/gen_dense1/kernel", "generator/gen_dense1/bias", "generator/gen_dense2/kernel",
+      "generator/gen_dense2/bias", "generator/gen_output/kernel", "generator/gen_output/bias",
+      "discriminator/disc_dense1/kernel", "discriminator/disc_dense1/bias",
+      "discriminator/disc_dense2/kernel", "discriminator/disc_dense2/bias",
+      "discriminator/disc_output/kernel", "discriminator/disc_output/bias"};
+  const int shp[12][2] = {{h->Z, h->Hg}, {1, h->Hg}, {h->Hg, h->Hg}, {1, h->Hg}, {h->Hg, h->G}, {1, h->G},
+                          {h->G, h->Hd}, {1, h->Hd}, {h->Hd, h->Hd}, {1, h->Hd}, {h->Hd, 1}, {1, 1}};
+  size_t off[2] = {0, 0};
+  for (int t = 0; t < 12; ++t) {
+    TensorDesc& d = h->td[t];
+    d.name = names[t]; d.net = t < 6 ? WGAN_NET_GENERATOR : WGAN_NET_CRITIC;
+    d.rows = shp[t][0]; d.cols = shp[t][1];
+    d.ld = (d.rows == 1) ? d.cols : wgan_padded_ld(d.cols);
+    d.offset = off[d.net];
+    off[d.net] += round64(static_cast<size_t>(d.rows) * d.ld);
+  }
+  for (int n = 0; n < 2; ++n) {
+    h->arena_n[n] = off[n] + 4;
+    for (int k = 0; k < 4; ++k) {
+      if (cudaMalloc(&h->arena[n][k], h->arena_n[n] * 4) != cudaSuccess) return fail("cudaMalloc(arena) failed");
+      cudaMemset(h->arena[n][k], 0, h->arena_n[n] * 4);
+    }
+    if (cudaMalloc(&h->powers[n], 16) != cudaSuccess) return fail("cudaMalloc(powers) failed");
+    float pw[4] = {cfg->beta1, cfg->beta2, 0.f, 0.f};        // beta powers start at beta [A:123-128]
+    cudaMemcpy(h->powers[n], pw, 16, cudaMemcpyHostToDevice);
+  }
+
+  // ---- workspace ----
+  const size_t R = h->R;
+  h->nsq_tiles_max = cdiv(h->G, 32);
+  struct { float** p; size_t n; } allocs[] = {
+      {&h->zbuf, R * h->Zl}, {&h->gh1, R * h->Hgl}, {&h->gh2, R * h->Hgl}, {&h->xcat, 3 * R * h->Gl},
+      {&h->h1, 3 * R * h->Hdl}, {&h->h2, 3 * R * h->Hdl}, {&h->d2, 3 * R * h->Hdl}, {&h->d1, 3 * R * h->Hdl},
+      {&h->dout, 3 * R}, {&h->v2, R * h->Hdl}, {&h->gd2, R * h->Hgl}, {&h->gd1, R * h->Hgl}, {&h->dz, R * h->Zl},
+      {&h->nsq, static_cast<size_t>(h->nsq_tiles_max) * R}, {&h->crow, R}, {&h->pen, R}, {&h->norms, R},
+      {&h->colpart, static_cast<size_t>(64) * (h->G > h->Hg ? (h->G > h->Hd ? h->G : h->Hd) : (h->Hg > h->Hd ? h->Hg : h->Hd))},
+      {&h->sample_tmp, R * h->Gl}};
+  for (auto& a : allocs) {
+    if (cudaMalloc(a.p, (a.n + 64) * 4) != cudaSuccess) return fail("cudaMalloc(workspace) failed (max_batch too large?)");
+    cudaMemset(*a.p, 0, (a.n + 64) * 4);
+  }
+  h->splitws_n = static_cast<size_t>(3 * h->num_sms + 8) * BM * 256;
+  {
+    // a two-part wgrad of the largest weight must fit with one slab per part
+    size_t w1 = round64(static_cast<size_t>(h->G) * h->Hdl), w3 = round64(static_cast<size_t>(h->Hg) * h->Gl);
+    size_t need = 2 * (w1 > w3 ? w1 : w3);
+    if (h->splitws_n < need) h->splitws_n = need;
+  }
+  if (cudaMalloc(&h->splitws, h->splitws_n * 4) != cudaSuccess) return fail("cudaMalloc(split workspace) failed");
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail("device error during create");
+  *out = h;
+  return 0;
+}
+
+int wgan_get_tensor_info(const wgan_handle* h, int index, wgan_tensor_info* out) {
+  if (!h || !out || index < 0 || index >= 12) return -2;
+  const TensorDesc& d = h->td[index];
+  memset(out, 0, sizeof *out);
+  strncpy(out->name, d.name, sizeof out->name - 1);
+  out->net = d.net; out->rows = d.rows; out->cols = d.cols; out->ld = d.ld;
+  out->offset = static_cast<int64_t>(d.offset);
+  return 0;
+}
+
+int wgan_get_tensor(wgan_handle* h, int kind, int index, float* host_dst) {
+  if (!h) return -2;
+  if (kind < 0 || kind > 3 || index < 0 || index >= 12 || !host_dst) FAIL("get_tensor: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const TensorDesc& d = h->td[index];
+  CK(cudaMemcpy2D(host_dst, static_cast<size_t>(d.cols) * 4, h->arena[d.net][kind] + d.offset,
+                  static_cast<size_t>(d.ld) * 4, static_cast<size_t>(d.cols) * 4, d.rows, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int wgan_set_tensor(wgan_handle* h, int kind, int index, const float* host_src) {
+  if (!h) return -2;
+  if (kind < 0 || kind > 3 || index < 0 || index >= 12 || !host_src) FAIL("set_tensor: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const TensorDesc& d = h->td[index];
+  CK(cudaMemcpy2D(h->arena[d.net][kind] + d.offset, static_cast<size_t>(d.ld) * 4, host_src,
+                  static_cast<size_t>(d.cols) * 4, static_cast<size_t>(d.cols) * 4, d.rows, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int wgan_get_adam_powers(wgan_handle* h, int net, float* b1p, float* b2p) {
+  if (!h) return -2;
+  if (net < 0 || net > 1 || !b1p || !b2p) FAIL("get_adam_powers: bad argument");
+  float pw[2];
+  CK(cudaMemcpy(pw, h->powers[net], 8, cudaMemcpyDeviceToHost));
+  *b1p = pw[0]; *b2p = pw[1];
+  return 0;
+}
+
+int wgan_set_adam_powers(wgan_handle* h, int net, float b1p, float b2p) {
+  if (!h) return -2;
+  if (net < 0 || net > 1) FAIL("set_adam_powers: bad argument");
+  float pw[2] = {b1p, b2p};
+  CK(cudaMemcpy(h->powers[net], pw, 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int wgan_get_arena(wgan_handle* h, int net, int kind, float** dev_ptr, size_t* n_floats) {
+  if (!h) return -2;
+  if (net < 0 || net > 1 || kind < 0 || kind > 3 || !dev_ptr || !n_floats) FAIL("get_arena: bad argument");
+  *dev_ptr = h->arena[net][kind];
+  *n_floats = h->arena_n[net];
+  return 0;
+}
+
+int wgan_get_scalars(wgan_handle* h, int net, float* host4, wgan_stream_t stream) {
+  if (!h) return -2;
+  if (net < 0 || net > 1 || !host4) FAIL("get_scalars: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaMemcpyAsync(host4, h->scalars(net), 16, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Critic step gradients  (reference: obj_d [W:137], var_list d_params [W:154])
+// ---------------------------------------------------------------------------------------------
+int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
+                      const float* eps_dev, int rows, int global_batch, wgan_stream_t stream) {
+  if (!h) return -2;
+  if (!x_dev || !z_dev) FAIL("critic_grads: null input");
+  TRY(check_rows(h, rows, global_batch));
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool gp = h->cfg.lambda_gp != 0.0f;
+  if (gp && !eps_dev) FAIL("critic_grads: eps required when lambda_gp != 0");
+  const int Bl = rows, nh = gp ? 1 : 0, T = (2 + nh) * Bl;
+  const int Hd = h->Hd, Hdl = h->Hdl, G = h->G, Gl = h->Gl;
+  const float a = h->cfg.alpha, invB = 1.0f / static_cast<float>(global_batch);
+  const int real0 = (1 + nh) * Bl;                       // first real row in the stacked buffers
+
+  // inputs into TMA-legal layouts
+  const float* z; int lz;
+  TRY(stage_input(h, z_dev, ldz, Bl, h->Z, h->zbuf, h->Zl, &z, &lz, s));
+  float* xreal_slot = h->xcat + static_cast<size_t>(real0) * Gl;
+  const float* x; int lx;
+  TRY(stage_input(h, x_dev, ldx, Bl, G, xreal_slot, Gl, &x, &lx, s));
+  const bool x_stacked = (x == xreal_slot && lx == Gl);
+
+  // generator forward (constant in this step)
+  float* xt = h->xcat;
+  TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
+  float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;    // interpolates, later overwritten by gx
+  if (gp) {
+    blend_kernel<<<ew_grid(static_cast<size_t>(Bl) * (Gl / 4), 256, h->num_sms), 256, 0, s>>>(
+        x, lx, xt, Gl, eps_dev, xh, Gl, Bl, Gl / 4);
+    TRY(post_launch(h, "blend_kernel"));
+  }
+
+  // critic layer 1 on [fake | hat | real]  [W:107-111]
+  const EpiParams e1 = epi_bias_lrelu(h->P(T_B1), a);
+  const float* W1 = h->P(T_W1); const int ldw1 = h->td[T_W1].ld;
+  if (x_stacked) {
+    TRY(gemm1(h, false, true, h->xcat, Gl, W1, ldw1, h->h1, Hdl, T, Hd, G, e1, s));
+  } else {
+    TRY(gemm1(h, false, true, h->xcat, Gl, W1, ldw1, h->h1, Hdl, real0, Hd, G, e1, s));
+    TRY(gemm1(h, false, true, x, lx, W1, ldw1, h->h1 + static_cast<size_t>(real0) * Hdl, Hdl, Bl, Hd, G, e1, s));
+  }
+  // layer 2  [W:113-117]
+  const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
+  TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, T, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
+  // layer 3 + upstream deltas  [W:119-123,137]
+  critic_head_kernel<<<ew_grid(static_cast<size_t>(T) * 32, 256, h->num_sms), 256, 0, s>>>(
+      h->h2, Hdl, T, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, invB, gp ? 1.0f : -invB,
+      gp ? -invB : 0.0f, a);
+  TRY(post_launch(h, "critic_head_kernel"));
+  float* sc = h->scalars(WGAN_NET_CRITIC);
+  segment_sum_kernel<<<1, 256, 0, s>>>(h->dout, Bl, 1, invB, 0.f, 0.f, sc + WGAN_S_DFAKE);
+  TRY(post_launch(h, "segment_sum_kernel"));
+  segment_sum_kernel<<<1, 256, 0, s>>>(h->dout + real0, Bl, 1, invB, 0.f, 0.f, sc + WGAN_S_DREAL);
+  TRY(post_launch(h, "segment_sum_kernel"));
+  // delta1 / g1 = (delta2 W2^T) . slope(h1)
+  TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, T, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
+
+  float* h1_hat = h->h1 + static_cast<size_t>(Bl) * Hdl;
+  float* h2_hat = h->h2 + static_cast<size_t>(Bl) * Hdl;
+  float* d1_hat = h->d1 + static_cast<size_t>(Bl) * Hdl;
+  if (gp) {
+    // input-gradient pass: gx = g1 W1^T, fused per-row sum of squares
+    EpiParams eg = epi_none();
+    eg.row_sumsq = h->nsq;
+    int tiles = 1;
+    TRY(gemm1(h, false, false, d1_hat, Hdl, W1, ldw1, xh, Gl, Bl, G, Hd, eg, s, &tiles));
+    h->last_gx_rows = Bl;
+    // norm, penalty, per-row coefficient; g1 <- c . g1
+    gp_coef_kernel<<<ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s>>>(
+        h->nsq, tiles, Bl, Bl, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, d1_hat, Hdl, Hd);
+    TRY(post_launch(h, "gp_coef_kernel"));
+    segment_sum_kernel<<<1, 256, 0, s>>>(h->pen, Bl, 1, h->cfg.lambda_gp * invB, 0.f, 0.f, sc + WGAN_S_GP);
+    TRY(post_launch(h, "segment_sum_kernel"));
+    // parameter-gradient-of-norm pass: v1 = c . (gx W1) . s1 (in place over h1_hat), v2 = (v1 W2) . s2
+    EpiParams ev1 = epi_mask(h1_hat, Hdl, a);
+    ev1.row_scale = h->crow;
+    TRY(gemm1(h, false, true, xh, Gl, W1, ldw1, h1_hat, Hdl, Bl, Hd, G, ev1, s));
+    TRY(gemm1(h, false, true, h1_hat, Hdl, W2, ldw2, h->v2, Hdl, Bl, Hd, Hd, epi_mask(h2_hat, Hdl, a), s));
+  } else {
+    CK(cudaMemsetAsync(sc + WGAN_S_GP, 0, 4, s));
+  }
+
+  // weight gradients
+  {
+    Part parts[2];
+    int np;
+    if (x_stacked) {
+      parts[0] = Part{h->xcat, Gl, h->d1, Hdl, T};
+      np = 1;
+    } else {
+      parts[0] = Part{h->xcat, Gl, h->d1, Hdl, real0};
+      parts[1] = Part{x, lx, h->d1 + static_cast<size_t>(real0) * Hdl, Hdl, Bl};
+      np = 2;
+    }
+    TRY(run_gemm(h, true, true, parts, np, h->Gr(T_W1), ldw1, G, Hd, epi_none(), nullptr, 0, s));
+  }
+  TRY(gemm1(h, true, true, h->h1, Hdl, h->d2, Hdl, h->Gr(T_W2), ldw2, Hd, Hd, T, epi_none(), s));
+  {
+    ColsumSeg sb[3] = {{h->d1, Bl, Hdl, 1.0f}, {h->d1 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, 1.0f}, {}};
+    TRY(colsum(h, sb, 2, Hd, h->Gr(T_B1), s));
+    ColsumSeg s2[3] = {{h->d2, Bl, Hdl, 1.0f}, {h->d2 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, 1.0f}, {}};
+    TRY(colsum(h, s2, 2, Hd, h->Gr(T_B2), s));
+    ColsumSeg s3[3] = {{h->h2, Bl, Hdl, invB}, {h->h2 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, -invB},
+                       {h->v2, Bl, Hdl, 1.0f}};
+    TRY(colsum(h, s3, gp ? 3 : 2, Hd, h->Gr(T_W3), s));
+    CK(cudaMemsetAsync(h->Gr(T_B3), 0, 4, s));           // sum(+1/B) + sum(-1/B) over equal row counts
+  }
+  return 0;
+}
+
+int wgan_critic_apply(wgan_handle* h, wgan_stream_t stream) {
+  if (!h) return -2;
+  CK(cudaSetDevice(h->cfg.device));
+  return adam_apply(h, WGAN_NET_CRITIC, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generator step gradients  (obj_g = -mean(D(G(z))) [W:138], var_list g_params [W:155])
+// ---------------------------------------------------------------------------------------------
+int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, int global_batch,
+                         wgan_stream_t stream) {
+  if (!h) return -2;
+  if (!z_dev) FAIL("generator_grads: null input");
+  TRY(check_rows(h, rows, global_batch));
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Bl = rows, Hd = h->Hd, Hdl = h->Hdl, G = h->G, Gl = h->Gl, Hg = h->Hg, Hgl = h->Hgl;
+  const float a = h->cfg.alpha, invB = 1.0f / static_cast<float>(global_batch);
+  const float* z; int lz;
+  TRY(stage_input(h, z_dev, ldz, Bl, h->Z, h->zbuf, h->Zl, &z, &lz, s));
+  float* xt = h->xcat;
+  float* d3 = h->xcat + static_cast<size_t>(Bl) * Gl;
+  TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
+  const float* W1 = h->P(T_W1); const int ldw1 = h->td[T_W1].ld;
+  const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
+  TRY(gemm1(h, false, true, xt, Gl, W1, ldw1, h->h1, Hdl, Bl, Hd, G, epi_bias_lrelu(h->P(T_B1), a), s));
+  TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, Bl, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
+  critic_head_kernel<<<ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s>>>(
+      h->h2, Hdl, Bl, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, -invB, 0.f, 0.f, a);
+  TRY(post_launch(h, "critic_head_kernel"));
+  float* sc = h->scalars(WGAN_NET_GENERATOR);
+  segment_sum_kernel<<<1, 256, 0, s>>>(h->dout, Bl, 1, invB, 0.f, 0.f, sc + WGAN_S_DFAKE);
+  TRY(post_launch(h, "segment_sum_kernel"));
+  // back through the critic to the generated cells
+  TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, Bl, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
+  TRY(gemm1(h, false, false, h->d1, Hdl, W1, ldw1, d3, Gl, Bl, G, Hd, epi_mask(xt, Gl, a), s));
+  // generator backward
+  const float* Wg3 = h->P(T_WG3); const int ldg3 = h->td[T_WG3].ld;
+  const float* Wg2 = h->P(T_WG2); const int ldg2 = h->td[T_WG2].ld;
+  TRY(gemm1(h, true, true, h->gh2, Hgl, d3, Gl, h->Gr(T_WG3), ldg3, Hg, G, Bl, epi_none(), s));
+  ColsumSeg c3[3] = {{d3, Bl, Gl, 1.0f}, {}, {}};
+  TRY(colsum(h, c3, 1, G, h->Gr(T_BG3), s));
+  TRY(gemm1(h, false, false, d3, Gl, Wg3, ldg3, h->gd2, Hgl, Bl, Hg, G, epi_mask(h->gh2, Hgl, a), s));
+  TRY(gemm1(h, true, true, h->gh1, Hgl, h->gd2, Hgl, h->Gr(T_WG2), ldg2, Hg, Hg, Bl, epi_none(), s));
+  ColsumSeg c2[3] = {{h->gd2, Bl, Hgl, 1.0f}, {}, {}};
+  TRY(colsum(h, c2, 1, Hg, h->Gr(T_BG2), s));
+  TRY(gemm1(h, false, false, h->gd2, Hgl, Wg2, ldg2, h->gd1, Hgl, Bl, Hg, Hg, epi_mask(h->gh1, Hgl, a), s));
+  TRY(gemm1(h, true, true, z, lz, h->gd1, Hgl, h->Gr(T_WG1), h->td[T_WG1].ld, h->Z, Hg, Bl, epi_none(), s));
+  ColsumSeg c1[3] = {{h->gd1, Bl, Hgl, 1.0f}, {}, {}};
+  TRY(colsum(h, c1, 1, Hg, h->Gr(T_BG1), s));
+  return 0;
+}
+
+int wgan_generator_apply(wgan_handle* h, wgan_stream_t stream) {
+  if (!h) return -2;
+  CK(cudaSetDevice(h->cfg.device));
+  return adam_apply(h, WGAN_NET_GENERATOR, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched sampler: out = G(z)   (generator forward only, [W:217])
+// ---------------------------------------------------------------------------------------------
+int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int ld_out, int rows,
+                wgan_stream_t stream) {
+  if (!h) return -2;
+  if (!z_dev || !out_dev) FAIL("sample: null argument");
+  TRY(check_rows(h, rows, rows));
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float* z; int lz;
+  TRY(stage_input(h, z_dev, ldz, rows, h->Z, h->zbuf, h->Zl, &z, &lz, s));
+  const bool direct = (reinterpret_cast<uintptr_t>(out_dev) & 15) == 0 && (ld_out & 3) == 0 && ld_out >= h->G;
+  if (direct) return generator_forward(h, z, lz, rows, out_dev, ld_out, s);
+  TRY(generator_forward(h, z, lz, rows, h->sample_tmp, h->Gl, s));
+  CK(cudaMemcpy2DAsync(out_dev, static_cast<size_t>(ld_out) * 4, h->sample_tmp, static_cast<size_t>(h->Gl) * 4,
+                       static_cast<size_t>(h->G) * 4, rows, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Latent-vector fit step (build-defined workload)
+// ---------------------------------------------------------------------------------------------
+int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_dev, float* powers_dev,
+                         const float* x_dev, int ldx, float* loss_dev, int rows, float learn_rate,
+                         wgan_stream_t stream) {
+  if (!h) return -2;
+  if (!z_dev || !m_dev || !v_dev || !powers_dev || !x_dev || !loss_dev) FAIL("latent_fit_step: null argument");
+  if (h->Z % 4 != 0) FAIL("latent_fit_step needs noise_input_size %% 4 == 0 (got %d)", h->Z);
+  if ((reinterpret_cast<uintptr_t>(z_dev) & 15) != 0) FAIL("latent_fit_step: z must be 16-byte aligned");
+  TRY(check_rows(h, rows, rows));
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Bl = rows, G = h->G, Gl = h->Gl, Hg = h->Hg, Hgl = h->Hgl, Z = h->Z;
+  const float a = h->cfg.alpha;
+  float* xt = h->xcat;
+  float* d3 = h->xcat + static_cast<size_t>(Bl) * Gl;
+  TRY(generator_forward(h, z_dev, Z, Bl, xt, Gl, s));
+  latent_residual_kernel<<<Bl, 256, 0, s>>>(xt, Gl, x_dev, ldx, d3, Gl, loss_dev, G, a);
+  TRY(post_launch(h, "latent_residual_kernel"));
+  const float* Wg3 = h->P(T_WG3); const float* Wg2 = h->P(T_WG2); const float* Wg1 = h->P(T_WG1);
+  TRY(gemm1(h, false, false, d3, Gl, Wg3, h->td[T_WG3].ld, h->gd2, Hgl, Bl, Hg, G, epi_mask(h->gh2, Hgl, a), s));
+  TRY(gemm1(h, false, false, h->gd2, Hgl, Wg2, h->td[T_WG2].ld, h->gd1, Hgl, Bl, Hg, Hg, epi_mask(h->gh1, Hgl, a), s));
+  TRY(gemm1(h, false, false, h->gd1, Hgl, Wg1, h->td[T_WG1].ld, h->dz, Z, Bl, Z, Hg, epi_none(), s));
+  const size_t n4 = static_cast<size_t>(Bl) * Z / 4;
+  adam_kernel<<<ew_grid(n4, 256, h->num_sms), 256, 0, s>>>(z_dev, h->dz, m_dev, v_dev, n4, powers_dev, learn_rate,
+                                                          h->cfg.beta1, h->cfg.beta2, h->cfg.epsilon);
+  TRY(post_launch(h, "adam_kernel"));
+  adam_finish_kernel<<<1, 32, 0, s>>>(powers_dev, h->cfg.beta1, h->cfg.beta2);
+  return post_launch(h, "adam_finish_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device input pipeline
+// ---------------------------------------------------------------------------------------------
+static int rng_launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_create_error = std::string(what) + ": " + cudaGetErrorString(e); return -3; }
+  return 0;
+}
+static int upload_poisson_cdf_once() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (done_dev == dev) return 0;
+  float cdf[12];
+  double acc = 0.0, term = exp(-1.0);
+  for (int k = 0; k < 12; ++k) { if (k > 0) term /= k; acc += term; cdf[k] = static_cast<float>(acc); }
+  if (cudaMemcpyToSymbol(c_poisson1_cdf, cdf, sizeof cdf) != cudaSuccess) return -1;
+  done_dev = dev;
+  return 0;
+}
+
+int wgan_rng_noise_prior(float* out_dev, int ld, int64_t row0, int rows, int dim, float sigma,
+                         uint64_t seed, uint32_t call_id, wgan_stream_t stream) {
+  if (!out_dev || rows <= 0 || dim <= 0 || ld < dim) { g_create_error = "rng_noise_prior: bad argument"; return -2; }
+  if (upload_poisson_cdf_once() != 0) { g_create_error = "rng_noise_prior: constant upload failed"; return -1; }
+  const size_t n = static_cast<size_t>(rows) * dim;
+  int grid = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  rng_noise_prior_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, ld, row0, rows, dim, sigma,
+                                                                               seed, call_id, 1u);
+  return rng_launch_check("rng_noise_prior_kernel");
+}
+
+int wgan_rng_uniform(float* out_dev, int64_t row0, int rows, uint64_t seed, uint32_t call_id,
+                     wgan_stream_t stream) {
+  if (!out_dev || rows <= 0) { g_create_error = "rng_uniform: bad argument"; return -2; }
+  rng_uniform_kernel<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, row0, rows, seed,
+                                                                                     call_id, 2u);
+  return rng_launch_check("rng_uniform_kernel");
+}
+
+int wgan_rng_indices(int64_t* out_dev, int64_t row0, int rows, uint32_t n_cells, uint64_t seed,
+                     uint32_t call_id, wgan_stream_t stream) {
+  if (!out_dev || rows <= 0 || n_cells == 0) { g_create_error = "rng_indices: bad argument"; return -2; }
+  rng_indices_kernel<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, row0, rows, n_cells,
+                                                                                     seed, call_id, 3u);
+  return rng_launch_check("rng_indices_kernel");
+}
+
+int wgan_gather_rows(const float* data_dev, int ld_data, const int64_t* idx_dev, float* out_dev,
+                     int ld_out, int rows, int cols, wgan_stream_t stream) {
+  if (!data_dev || !idx_dev || !out_dev || rows <= 0 || cols <= 0) { g_create_error = "gather_rows: bad argument"; return -2; }
+  if ((ld_data & 3) || (ld_out & 3) || (reinterpret_cast<uintptr_t>(data_dev) & 15) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) {
+    g_create_error = "gather_rows: data and out must be 16-byte aligned with ld % 4 == 0";
+    return -2;
+  }
+  const int cols4 = round4(cols) / 4;
+  if (round4(cols) > ld_data || round4(cols) > ld_out) { g_create_error = "gather_rows: ld smaller than padded cols"; return -2; }
+  const size_t n = static_cast<size_t>(rows) * cols4;
+  int grid = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(data_dev, ld_data, idx_dev, out_dev,
+                                                                           ld_out, rows, cols4);
+  return rng_launch_check("gather_rows_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Test hooks
+// ---------------------------------------------------------------------------------------------
+int wgan_gemm(wgan_handle* h, int a_mn, int b_mn, const float* A, int lda, const float* B, int ldb,
+              float* D, int ldd, int M, int N, int K, const float* bias, int act, const float* aux,
+              int ld_aux, const float* row_scale, float* row_sumsq, int* sumsq_tiles,
+              int force_splits, wgan_stream_t stream) {
+  if (!h) return -2;
+  CK(cudaSetDevice(h->cfg.device));
+  EpiParams e = epi_none();
+  e.bias = bias; e.act = act; e.aux = aux; e.ld_aux = ld_aux; e.row_scale = row_scale;
+  e.row_sumsq = row_sumsq; e.alpha = h->cfg.alpha;
+  Part p{A, lda, B, ldb, K};
+  return run_gemm(h, a_mn != 0, b_mn != 0, &p, 1, D, ldd, M, N, e, sumsq_tiles, force_splits,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int wgan_get_buffer(wgan_handle* h, const char* name, float** dev_ptr, int* rows, int* cols, int* ld) {
+  if (!h) return -2;
+  if (!name || !dev_ptr || !rows || !cols || !ld) FAIL("get_buffer: null argument");
+  const int Bl = h->last_gx_rows;
+  std::string n(name);
+  if (n == "x_tilde") { *dev_ptr = h->xcat; *rows = h->R; *cols = h->G; *ld = h->Gl; }
+  else if (n == "gx") { *dev_ptr = h->xcat + static_cast<size_t>(Bl) * h->Gl; *rows = Bl; *cols = h->G; *ld = h->Gl; }
+  else if (n == "norms") { *dev_ptr = h->norms; *rows = 1; *cols = Bl; *ld = Bl; }
+  else if (n == "d") { *dev_ptr = h->dout; *rows = 1; *cols = 3 * h->R; *ld = 3 * h->R; }
+  else if (n == "h1") { *dev_ptr = h->h1; *rows = 3 * h->R; *cols = h->Hd; *ld = h->Hdl; }
+  else if (n == "h2") { *dev_ptr = h->h2; *rows = 3 * h->R; *cols = h->Hd; *ld = h->Hdl; }
+  else FAIL("get_buffer: unknown buffer '%s'", name);
+  return 0;
+}
+
+}  // extern "C"

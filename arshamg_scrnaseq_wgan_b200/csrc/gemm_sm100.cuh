@@ -1,0 +1,384 @@
+// TF32 tensor-core GEMM for sm_100a: TMA-fed, tcgen05.mma with the accumulator in TMEM,
+// persistent warp-specialised CTAs (1 TMA warp, 1 MMA warp, 4 epilogue warps), fused
+// bias / LeakyReLU / slope-mask / row-scale / row-sum-of-squares epilogue, TMA store.
+//
+// Computes, for every split z of the K range,
+//      D[z][m, n] = epi( sum_{k in split z} A(m, k) * B(n, k) )
+// where A and B are fp32 matrices in global memory read as TF32 by TMA
+// (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), each either "K-major" (K contiguous) or "MN-major"
+// (M resp. N contiguous).  This covers the three dense-layer products of the reference graph
+// with row-major activations [rows, features] and tf.layers.dense kernels [in, out]:
+//      forward   Y  = X  * W      A = X  (K-major),  B = W  (MN-major)   [W:65,71,77,107,113,119]
+//      dgrad     dX = dY * W^T    A = dY (K-major),  B = W  (K-major)    (tf.gradients, [W:154-155])
+//      wgrad     dW = X^T * dY    A = X  (MN-major), B = dY (MN-major)
+// The epilogue (only applied when splits == 1; split-K partials are finished by
+// finish_splitk_kernel in kernels.cu with the same EpiParams) is
+//      y = acc (+ bias[n]);  y = leaky_relu(y);  y *= slope(aux[m,n]);  y *= row_scale[m]
+//      row_sumsq[n_tile][m] = sum_n y^2
+// where slope(h) = h > 0 ? 1 : alpha recovers phi'(a) from the post-activation.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wg {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 32;           // 32 tf32 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;        // 32 B / sizeof(tf32)
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int EPI_BOX_BYTES = 32 * 32 * 4;   // one [32 rows][32 cols] fp32 staging box
+constexpr int EPI_BUFS = 8;                   // 4 epilogue warps x 2
+
+struct EpiParams {
+  const float* bias;        // [N] or nullptr
+  const float* aux;         // [M, ld_aux] post-activation whose sign picks the LeakyReLU slope, or nullptr
+  const float* row_scale;   // [M] or nullptr
+  float* row_sumsq;         // [n_tiles, M] partial sums of y^2 per N tile, or nullptr
+  int ld_aux;
+  int act;                  // 0 = identity, 1 = LeakyReLU(alpha)
+  float alpha;
+  int pad_;
+};
+
+struct GemmParams {
+  CUtensorMap tma_a;        // 64 B aligned by the driver type
+  CUtensorMap tma_b;
+  CUtensorMap tma_d;        // 3-D (N, M, splits) fp32, box (32, 32, 1), SWIZZLE_128B
+  int M, N, K;
+  int bn;                   // N tile, multiple of 32, <= 256
+  int splits;
+  int kb_per_split;         // k-blocks (of BK) per split
+  int m_tiles, n_tiles;
+  int stages;
+  int total_kb;
+  EpiParams epi;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, descriptor version 1 = Blackwell).
+//   K-major : rows of 128 B (32 tf32 of K), 8-row swizzle atoms 1024 B apart (SBO); LBO unused.
+//   MN-major: a [32 k-rows][32 mn] box per 32 MN elements; boxes 4096 B apart (LBO), the 8-k-row
+//             atoms inside a box 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;          // descriptor version (sm_100)
+  d |= 2ull << 61;          // SWIZZLE_128B
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel.  Dynamic smem (after 1024 B alignment):
+//   [stages] x { A tile 128 x 128 B | B tile bn x 128 B }, 8 x 4 KB epilogue boxes,
+//   full[8], empty[8], tmem_full[2], tmem_empty[2] mbarriers, tmem base pointer.
+// ---------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = BM * 128u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t epi_base = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
+  const uint32_t bar_base = epi_base + EPI_BUFS * EPI_BOX_BYTES;
+  const uint32_t full_bar = bar_base;                       // 8 x 8 B
+  const uint32_t empty_bar = bar_base + 64;                 // 8 x 8 B
+  const uint32_t tfull_bar = bar_base + 128;                // 2 x 8 B
+  const uint32_t tempty_bar = bar_base + 144;               // 2 x 8 B
+  const uint32_t tmem_slot = bar_base + 160;                // 4 B
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tma_a);
+    prefetch_tmap(&p.tma_b);
+    prefetch_tmap(&p.tma_d);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(full_bar + 8 * s, 1);
+        mbar_init(empty_bar + 8 * s, 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar + 8 * a, 1);
+        mbar_init(tempty_bar + 8 * a, 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    // 2 accumulators of bn <= 256 fp32 columns: allocate all 512 columns (1 CTA per SM).
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = (tile / p.n_tiles) % p.m_tiles;
+        const int z = tile / (p.n_tiles * p.m_tiles);
+        const int m0 = mt * BM, n0 = nt * p.bn;
+        const int kb0 = z * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_2d(sa, &p.tma_a, fb, k0, m0);                       // box [128 rows][32 k]
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c)                            // boxes [32 k][32 m]
+              tma_load_2d(sa + c * 4096, &p.tma_a, fb, m0 + 32 * c, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &p.tma_b, fb, k0, n0);                       // box [bn rows][32 k]
+          } else {
+            for (int c = 0; c < p.bn / 32; ++c)                          // boxes [32 k][32 n]
+              tma_load_2d(sb + c * 4096, &p.tma_b, fb, n0 + 32 * c, k0);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | (static_cast<uint32_t>(p.bn >> 3) << 17) |
+                             (static_cast<uint32_t>(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int z = tile / (p.n_tiles * p.m_tiles);
+        const int kb0 = z * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
+        tcgen05_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.bn);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tcgen05_after_sync();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int s = 0; s < BK / UMMA_K; ++s) {
+            const uint64_t adesc = A_MN ? make_smem_desc(sa + s * 1024, 4096, 1024)
+                                        : make_smem_desc(sa + s * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(sb + s * 1024, 4096, 1024)
+                                        : make_smem_desc(sb + s * 32, 16, 1024);
+            umma_tf32(d_tmem, adesc, bdesc, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);      // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar + 8 * acc);          // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (TMEM -> regs -> smem -> TMA store) =====================
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const EpiParams& e = p.epi;
+    const bool fused = (p.splits == 1);
+    uint32_t nstore = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int z = tile / (p.n_tiles * p.m_tiles);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row0 = mt * BM + 32 * q;
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tcgen05_after_sync();
+      float rs = 1.0f;
+      if (fused && e.row_scale != nullptr && row_ok) rs = __ldg(e.row_scale + row);
+      float sumsq = 0.0f;
+      if (row0 < p.M) {
+        const int nchunks = p.bn / 32;
+        for (int c = 0; c < nchunks; ++c) {
+          const int n0 = nt * p.bn + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) +
+                        static_cast<uint32_t>(acc * p.bn + c * 32), v);
+          if (fused) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + j;
+              float y = __uint_as_float(v[j]);
+              if (e.bias != nullptr && n < p.N) y += __ldg(e.bias + n);
+              if (e.act == 1) y = fmaxf(y, e.alpha * y);
+              if (e.aux != nullptr) {
+                float h = 1.0f;
+                if (row_ok && n < p.N) h = __ldg(e.aux + static_cast<size_t>(row) * e.ld_aux + n);
+                y *= (h > 0.0f) ? 1.0f : e.alpha;
+              }
+              y *= rs;
+              if (n < p.N) sumsq += y * y;
+              v[j] = __float_as_uint(y);
+            }
+          }
+          const uint32_t buf = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
+          if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago is free again
+          __syncwarp();
+          const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = rbase + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);   // SWIZZLE_128B
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
+                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&p.tma_d, buf, n0, row0, z);
+            tma_store_commit();
+          }
+          ++nstore;
+        }
+      }
+      // all of this warp's TMEM reads for the tile are done: hand the accumulator back
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (fused && e.row_sumsq != nullptr && row_ok)
+        e.row_sumsq[static_cast<size_t>(nt) * p.M + row] = sumsq;
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+                 : "memory");
+  }
+}
+
+}  // namespace wg

@@ -1,0 +1,407 @@
+// Non-GEMM device kernels of the WGAN(-GP) hot path: split-K finish, FP32 verification GEMM,
+// critic head (layer-3 row dot + loss partials + delta/g2 construction), gradient-penalty
+// coefficient, interpolate blend, column sums (bias grads), fused multi-tensor TF-Adam,
+// Philox RNG (noise prior / epsilon / cell indices), row gather, latent-fit residual.
+// Reference semantics: losses [W:137-138], LeakyReLU [W:69..117], Adam [A:140-151,214-225],
+// prior [W:91-94], minibatch gather [W:188-191].  Math per SURVEY Appendix A.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gemm_sm100.cuh"
+
+namespace wg {
+
+// ---------------------------------------------------------------------------------------------
+// Split-K finish: out[m,n] = epi(sum_s part[s][m,n]).  Also the epilogue of the FP32
+// verification GEMM (splits = 1, part == out allowed: same thread reads then writes).
+// row_sumsq (if requested) is written as a single "tile" (n_tiles = 1): one warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void finish_splitk_kernel(const float* __restrict__ part, size_t slab_stride, int splits,
+                                     float* out, int ld, int M, int N, EpiParams e) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
+       row += gridDim.x * warps_per_block) {
+    const float rs = e.row_scale ? e.row_scale[row] : 1.0f;
+    float sumsq = 0.0f;
+    for (int n = lane; n < N; n += 32) {
+      const size_t off = static_cast<size_t>(row) * ld + n;
+      float y = 0.0f;
+      for (int s = 0; s < splits; ++s) y += part[s * slab_stride + off];
+      if (e.bias) y += e.bias[n];
+      if (e.act == 1) y = fmaxf(y, e.alpha * y);
+      if (e.aux) {
+        const float h = e.aux[static_cast<size_t>(row) * e.ld_aux + n];
+        y *= (h > 0.0f) ? 1.0f : e.alpha;
+      }
+      y *= rs;
+      sumsq += y * y;
+      out[off] = y;
+    }
+    if (e.row_sumsq) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
+      if (lane == 0) e.row_sumsq[row] = sumsq;
+    }
+  }
+}
+
+// Sum `splits` slabs of a weight-gradient sized [rows, ld] (pads included) into the grad arena.
+__global__ void reduce_slabs_kernel(const float* __restrict__ part, size_t slab_stride, int splits,
+                                    float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float y = 0.0f;
+    for (int s = 0; s < splits; ++s) y += part[s * slab_stride + i];
+    out[i] = y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 CUDA-core GEMM (verification mode only: separates algorithm bugs from TF32 rounding).
+// C[m,n] = sum_k A(m,k) B(n,k), element (m,k) of A at A[m*sam + k*sak], same for B.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_fp32_kernel(const float* __restrict__ A, long sam, long sak, const float* __restrict__ B,
+                 long sbn, long sbk, float* __restrict__ C, int ldc, int M, int N, int K) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Bs[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int mm, kk;
+      if (sak == 1) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < K) ? A[m * sam + k * sak] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int nn, kk;
+      if (sbk == 1) { kk = i & 15; nn = i >> 4; } else { nn = i & 63; kk = i >> 6; }
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < N && k < K) ? B[n * sbn + k * sbk] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) C[static_cast<size_t>(m) * ldc + n] = acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Critic head.  One warp per row r of h2 [rows, ld]:
+//   d[r]     = h2[r,:] . w3 + b3                                   [W:119-123]
+//   dlt[r,j] = coef(r) * w3[j] * slope(h2[r,j])                    (delta2 / g2)
+// Rows are split in three consecutive segments of `seg` rows with coefficients c0, c1, c2
+// (fake: +1/B, interpolate: 1, real: -1/B; nseg in {1,2,3}).
+// ---------------------------------------------------------------------------------------------
+__global__ void critic_head_kernel(const float* __restrict__ h2, int ld, int rows, int H,
+                                   const float* __restrict__ w3, const float* __restrict__ b3,
+                                   float* __restrict__ d, float* __restrict__ dlt, int seg, float c0,
+                                   float c1, float c2, float alpha) {
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int s = r / seg;
+    const float coef = s == 0 ? c0 : (s == 1 ? c1 : c2);
+    const float* hr = h2 + static_cast<size_t>(r) * ld;
+    float* dr = dlt + static_cast<size_t>(r) * ld;
+    float acc = 0.0f;
+    for (int j = lane; j < H; j += 32) {
+      const float h = hr[j], w = w3[j];
+      acc = fmaf(h, w, acc);
+      dr[j] = coef * w * ((h > 0.0f) ? 1.0f : alpha);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) d[r] = acc + b3[0];
+  }
+}
+
+// Deterministic single-block segmented sum: out[i] = scale[i] * sum(d[i*seg .. (i+1)*seg)), i < nseg.
+__global__ void segment_sum_kernel(const float* __restrict__ d, int seg, int nseg, float s0, float s1,
+                                   float s2, float* __restrict__ out) {
+  __shared__ float red[32];
+  for (int g = 0; g < nseg; ++g) {
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < seg; i += blockDim.x) acc += d[static_cast<size_t>(g) * seg + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) out[g] = v * (g == 0 ? s0 : (g == 1 ? s1 : s2));
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gradient-penalty coefficient.  One warp per interpolate row b:
+//   n_b = sqrt(sum_t nsq[t][b]);  c_b = lambda * 2/B * (n_b - 1) / n_b;  g1[b,:] *= c_b
+//   pen[b] = (n_b - 1)^2   (summed later by segment_sum_kernel with scale lambda/B)
+// ---------------------------------------------------------------------------------------------
+__global__ void gp_coef_kernel(const float* __restrict__ nsq, int ntiles, int tile_stride, int rows,
+                               float two_lambda_over_B, float* __restrict__ c, float* __restrict__ pen,
+                               float* __restrict__ norms, float* __restrict__ g1, int ld, int H) {
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    float s = 0.0f;
+    for (int t = 0; t < ntiles; ++t) s += nsq[static_cast<size_t>(t) * tile_stride + r];
+    const float n = sqrtf(s);
+    const float cb = two_lambda_over_B * (n - 1.0f) / n;
+    if (lane == 0) {
+      c[r] = cb;
+      pen[r] = (n - 1.0f) * (n - 1.0f);
+      norms[r] = n;
+    }
+    float* gr = g1 + static_cast<size_t>(r) * ld;
+    for (int j = lane; j < H; j += 32) gr[j] *= cb;
+  }
+}
+
+// x_hat[b,:] = eps[b] * x[b,:] + (1 - eps[b]) * x_tilde[b,:]      (SURVEY A.4), float4 over padded rows
+__global__ void blend_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ xt,
+                             int ldt, const float* __restrict__ eps, float* __restrict__ xh, int ldh,
+                             int rows, int cols4) {
+  const size_t total = static_cast<size_t>(rows) * cols4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols4), c = static_cast<int>(i % cols4) * 4;
+    const float e = eps[r], f = 1.0f - e;
+    const float4 a = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ldx + c);
+    const float4 b = *reinterpret_cast<const float4*>(xt + static_cast<size_t>(r) * ldt + c);
+    float4 o;
+    o.x = e * a.x + f * b.x;
+    o.y = e * a.y + f * b.y;
+    o.z = e * a.z + f * b.z;
+    o.w = e * a.w + f * b.w;
+    *reinterpret_cast<float4*>(xh + static_cast<size_t>(r) * ldh + c) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column sums over up to three row segments (bias grads, d w3):
+//   out[n] = sum_seg scale_seg * sum_r X_seg[r, n]
+// Stage 1: grid (ceil(N/32), RC): block (32 cols x 8 row lanes) -> part[rc][n].  Stage 2 sums RC.
+// ---------------------------------------------------------------------------------------------
+struct ColsumSeg {
+  const float* ptr;
+  int rows;
+  int ld;
+  float scale;
+};
+struct ColsumArgs {
+  ColsumSeg seg[3];
+  int nseg;
+  int N;
+};
+
+__global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int RC = gridDim.y, rc = blockIdx.y;
+  float acc = 0.0f;
+  if (n < a.N) {
+    for (int s = 0; s < a.nseg; ++s) {
+      const ColsumSeg sg = a.seg[s];
+      const int per = (sg.rows + RC - 1) / RC;
+      const int r0 = rc * per, r1 = min(r0 + per, sg.rows);
+      float t = 0.0f;
+      for (int r = r0 + ty; r < r1; r += 8) t += sg.ptr[static_cast<size_t>(r) * sg.ld + n];
+      acc += sg.scale * t;
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < a.N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    part[static_cast<size_t>(rc) * a.N + n] = t;
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ part, int RC, int N,
+                                    float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.0f;
+  for (int r = 0; r < RC; ++r) t += part[static_cast<size_t>(r) * N + n];
+  out[n] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused multi-tensor TF-Adam over a flat arena (params/grads/m/v share one layout) [A:140-151]:
+//   lr_t = lr * sqrt(1 - b2p) / (1 - b1p);  m += (g - m)(1 - b1);  v += (g*g - v)(1 - b2)
+//   var -= (m * lr_t) / (sqrt(v) + eps)            (epsilon OUTSIDE the bias correction)
+// Explicit _rn intrinsics: no FMA contraction, so the update is bit-identical to the FP32 oracle.
+// The beta powers live on the device (pw[0] = b1p, pw[1] = b2p) and are advanced by
+// adam_finish_kernel once all tensors are updated [A:214-225].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr_t,
+                                         float omb1, float omb2, float eps) {
+  m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
+  v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), omb2));
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m, lr_t), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n4, const float* __restrict__ pw, float lr,
+                            float beta1, float beta2, float eps) {
+  const float b1p = pw[0], b2p = pw[1];
+  const float lr_t = __fdiv_rn(__fmul_rn(lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+  const float omb1 = __fsub_rn(1.0f, beta1), omb2 = __fsub_rn(1.0f, beta2);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, lr_t, omb1, omb2, eps);
+    adam_one(pp.y, gg.y, mm.y, vv.y, lr_t, omb1, omb2, eps);
+    adam_one(pp.z, gg.z, mm.z, vv.z, lr_t, omb1, omb2, eps);
+    adam_one(pp.w, gg.w, mm.w, vv.w, lr_t, omb1, omb2, eps);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+
+__global__ void adam_finish_kernel(float* pw, float beta1, float beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    pw[0] = __fmul_rn(pw[0], beta1);
+    pw[1] = __fmul_rn(pw[1], beta2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (replaces the reference's unseeded global NumPy RNG [W:92-93,188]).
+// counter = (idx_lo, idx_hi, call_id, stream), key = seed; identical to oracle/wgan_oracle.py.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__constant__ float c_poisson1_cdf[12];
+
+// noise_prior: |Normal(0, sigma) + Poisson(1)|  [W:91-94]; element index = global_row*dim + col.
+__global__ void rng_noise_prior_kernel(float* __restrict__ out, int ld, long row0, int rows, int dim,
+                                       float sigma, uint64_t seed, uint32_t call_id, uint32_t stream) {
+  const size_t total = static_cast<size_t>(rows) * dim;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / dim), c = static_cast<int>(i % dim);
+    const uint64_t idx = static_cast<uint64_t>(row0 + r) * static_cast<uint64_t>(dim) + c;
+    const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32),
+                                               call_id, stream),
+                                    make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const float u1 = __fmul_rn(__fadd_rn(static_cast<float>(rnd.x >> 8), 0.5f), 5.9604644775390625e-8f);
+    const float u2 = __fmul_rn(__fadd_rn(static_cast<float>(rnd.y >> 8), 0.5f), 5.9604644775390625e-8f);
+    const float u3 = __fmul_rn(static_cast<float>(rnd.z >> 8), 5.9604644775390625e-8f);
+    const float normal = __fmul_rn(sqrtf(__fmul_rn(-2.0f, logf(u1))), cosf(__fmul_rn(6.2831854820251465f, u2)));
+    float pois = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) pois += (u3 >= c_poisson1_cdf[k]) ? 1.0f : 0.0f;
+    out[static_cast<size_t>(r) * ld + c] = fabsf(__fadd_rn(__fmul_rn(sigma, normal), pois));
+  }
+}
+
+// U[0,1) per global row (epsilon of the interpolates).
+__global__ void rng_uniform_kernel(float* __restrict__ out, long row0, int rows, uint64_t seed,
+                                   uint32_t call_id, uint32_t stream) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const uint64_t idx = static_cast<uint64_t>(row0 + r);
+  const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), call_id, stream),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  out[r] = __fmul_rn(static_cast<float>(rnd.x >> 8), 5.9604644775390625e-8f);
+}
+
+// Uniform-with-replacement cell indices in [0, n_cells)  [W:188].
+__global__ void rng_indices_kernel(int64_t* __restrict__ out, long row0, int rows, uint32_t n_cells,
+                                   uint64_t seed, uint32_t call_id, uint32_t stream) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const uint64_t idx = static_cast<uint64_t>(row0 + r);
+  const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), call_id, stream),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  out[r] = static_cast<int64_t>((static_cast<uint64_t>(rnd.x) * n_cells) >> 32);
+}
+
+// Minibatch gather from the resident cells-major matrix: out[r,:] = data[idx[r],:]  [W:188-191]
+__global__ void gather_rows_kernel(const float* __restrict__ data, int ldd, const int64_t* __restrict__ idx,
+                                   float* __restrict__ out, int ldo, int rows, int cols4) {
+  const size_t total = static_cast<size_t>(rows) * cols4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols4), c = static_cast<int>(i % cols4) * 4;
+    const int64_t src = idx[r];
+    *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * ldo + c) =
+        *reinterpret_cast<const float4*>(data + static_cast<size_t>(src) * ldd + c);
+  }
+}
+
+// Latent fit (build-defined): r = G(z) - x; loss[b] = sum r^2; d3 = 2 r slope(G(z)).
+// One block per row.
+__global__ void latent_residual_kernel(const float* __restrict__ xt, int ldt, const float* __restrict__ x,
+                                       int ldx, float* __restrict__ d3, int ldd, float* __restrict__ loss,
+                                       int cols, float alpha) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  float acc = 0.0f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float g = xt[static_cast<size_t>(r) * ldt + c];
+    const float d = g - x[static_cast<size_t>(r) * ldx + c];
+    acc += d * d;
+    d3[static_cast<size_t>(r) * ldd + c] = 2.0f * d * ((g > 0.0f) ? 1.0f : alpha);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) loss[r] = v;
+  }
+}
+
+}  // namespace wg

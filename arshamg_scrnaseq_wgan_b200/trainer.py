@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference script's interface for the hot path.
+
+Names follow scripts/WGAN-GP_minimal.py: the module constants [W:9-24] are ``WGANConfig``
+fields, ``generator`` / ``discriminator`` / ``noise_prior`` keep their names and argument
+meaning [W:61,91,103], variables keep their TF names [W:63-122], and the optimizer keeps the
+``Adam_Prediction_Optimizer`` signature [A:38-39].  All arithmetic happens in the sm_100a CUDA
+library behind include/wgan_b200.h (loaded through ctypes); PyTorch is used only for device
+memory, streams and ``torch.distributed``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PARAM_NAMES = (
+    "generator/gen_dense1/kernel", "generator/gen_dense1/bias",
+    "generator/gen_dense2/kernel", "generator/gen_dense2/bias",
+    "generator/gen_output/kernel", "generator/gen_output/bias",
+    "discriminator/disc_dense1/kernel", "discriminator/disc_dense1/bias",
+    "discriminator/disc_dense2/kernel", "discriminator/disc_dense2/bias",
+    "discriminator/disc_output/kernel", "discriminator/disc_output/bias",
+)
+GEN_NAMES, CRITIC_NAMES = PARAM_NAMES[:6], PARAM_NAMES[6:]
+NET_GENERATOR, NET_CRITIC = 0, 1
+KIND_PARAM, KIND_GRAD, KIND_M, KIND_V = 0, 1, 2, 3
+KINDS = {"param": 0, "grad": 1, "m": 2, "v": 3}
+
+
+@dataclasses.dataclass
+class Adam_Prediction_Optimizer:
+    """Hyper-parameter record with the reference constructor's signature [A:38-39].
+
+    ``prediction`` is accepted for API parity; all gradients of this model are dense, so the
+    reference's prediction branch (sparse path only, [A:189-194]) never runs."""
+    learning_rate: float = 0.001
+    beta1: float = 0.9
+    beta2: float = 0.999
+    epsilon: float = 1e-8
+    prediction: bool = False
+    use_locking: bool = False
+    name: str = "Adam"
+
+
+@dataclasses.dataclass
+class WGANConfig:
+    n_train_steps: int = 10000          # [W:9]
+    batch_size: int = 32                # [W:11]
+    noise_input_size: int = 100         # [W:13]
+    inflate_to_size: int = 600          # [W:14]
+    gex_size: int = 6605                # [W:15]
+    disc_internal_size: int = 200       # [W:17]
+    num_cells_train: int = 1500         # [W:18]
+    num_cells_generate: int = 500       # [W:20]
+    learn_rate: float = 1e-5            # [W:22]
+    beta1: float = 0.9                  # [W:154-155]
+    beta2: float = 0.999
+    epsilon: float = 1e-8               # [A:38]
+    alpha: float = 0.2                  # tf.nn.leaky_relu default
+    lambda_gp: float = 10.0             # build-defined; 0 => reference-literal
+    n_critic: int = 5                   # build-defined; 1 => reference-literal
+    step_order: str = "critic_first"    # "gen_first" => reference-literal [W:196,199]
+
+    @classmethod
+    def reference_literal(cls, **kw) -> "WGANConfig":
+        """Exactly what the reference script computes: no penalty, 1:1 updates, generator first."""
+        return cls(lambda_gp=0.0, n_critic=1, step_order="gen_first", **kw)
+
+
+class _DevPtr:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned memory."""
+
+    def __init__(self, ptr: int, n: int, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class WGANTrainer:
+    """One handle per GPU / per process.  Data-parallel when torch.distributed is initialised:
+    every rank passes its batch shard, gradients are SUM-all-reduced (one collective per
+    optimizer step over the flat gradient arena) and Adam runs replicated."""
+
+    def __init__(self, cfg: WGANConfig, max_batch: Optional[int] = None, device: Optional[int] = None,
+                 gemm_mode: int = 0, optimizer: Optional[Adam_Prediction_Optimizer] = None,
+                 process_group=None, distributed: Optional[bool] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("WGANTrainer needs a CUDA device (B200); there is no CPU fallback")
+        self.cfg = cfg
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        torch.cuda.set_device(self.device)
+        self.max_batch = int(max_batch if max_batch is not None else cfg.batch_size)
+        if optimizer is not None:
+            cfg = dataclasses.replace(cfg, learn_rate=optimizer.learning_rate, beta1=optimizer.beta1,
+                                      beta2=optimizer.beta2, epsilon=optimizer.epsilon)
+            self.cfg = cfg
+        c = _lib.WganConfig(cfg.noise_input_size, cfg.inflate_to_size, cfg.gex_size, cfg.disc_internal_size,
+                            self.max_batch, self.device, gemm_mode, 0, cfg.learn_rate, cfg.beta1, cfg.beta2,
+                            cfg.epsilon, cfg.alpha, cfg.lambda_gp, 0.0, 0.0)
+        self._h = C.c_void_p()
+        rc = self.lib.wgan_create(C.byref(c), C.byref(self._h))
+        if rc != 0:
+            raise _lib.WganError("wgan_create failed: " + self.lib.wgan_last_error(None).decode())
+        self.info = {}
+        for i in range(self.lib.wgan_tensor_count()):
+            ti = _lib.WganTensorInfo()
+            self._ck(self.lib.wgan_get_tensor_info(self._h, i, C.byref(ti)), "get_tensor_info")
+            self.info[ti.name.decode()] = (i, ti.net, ti.rows, ti.cols, ti.ld, ti.offset)
+        self.Gl = self.lib.wgan_padded_ld(cfg.gex_size)
+        # data parallel plumbing
+        import torch.distributed as dist
+        self.dist = dist
+        use_dist = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if use_dist else 1
+        self.rank = dist.get_rank(process_group) if use_dist else 0
+        self._grad_arena = {n: self.arena(n, KIND_GRAD) for n in (NET_GENERATOR, NET_CRITIC)}
+        self._data = None
+        self._calls = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc, what):
+        _lib.check(self.lib, self._h, rc, what)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.wgan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def arena(self, net: int, kind: int) -> torch.Tensor:
+        """Flat fp32 view of one arena (library-owned memory)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.wgan_get_arena(self._h, net, kind, C.byref(p), C.byref(n)), "get_arena")
+        return torch.as_tensor(_DevPtr(p.value, n.value), device=f"cuda:{self.device}")
+
+    def buffer(self, name: str) -> torch.Tensor:
+        p, r, c, ld = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.wgan_get_buffer(self._h, name.encode(), C.byref(p), C.byref(r), C.byref(c), C.byref(ld)),
+                 "get_buffer")
+        flat = torch.as_tensor(_DevPtr(p.value, r.value * ld.value), device=f"cuda:{self.device}")
+        return flat.view(r.value, ld.value)[:, :c.value]
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.wgan_launch_count(self._h))
+
+    # ------------------------------------------------------------------ state I/O
+    def get_tensor(self, name: str, kind: str = "param") -> np.ndarray:
+        i, _, rows, cols, _, _ = self.info[name]
+        out = np.empty((rows, cols), np.float32)
+        self._ck(self.lib.wgan_get_tensor(self._h, KINDS[kind], i, out.ctypes.data_as(C.c_void_p)), "get_tensor")
+        return out[0] if name.endswith("bias") else out
+
+    def set_tensor(self, name: str, value, kind: str = "param"):
+        i, _, rows, cols, _, _ = self.info[name]
+        v = np.ascontiguousarray(np.asarray(value, np.float32).reshape(rows, cols))
+        self._ck(self.lib.wgan_set_tensor(self._h, KINDS[kind], i, v.ctypes.data_as(C.c_void_p)), "set_tensor")
+
+    def set_params(self, params: Dict[str, np.ndarray]):
+        for k, v in params.items():
+            self.set_tensor(k, v)
+
+    def get_params(self) -> Dict[str, np.ndarray]:
+        return {k: self.get_tensor(k) for k in PARAM_NAMES}
+
+    def get_grads(self, names=PARAM_NAMES) -> Dict[str, np.ndarray]:
+        return {k: self.get_tensor(k, "grad") for k in names}
+
+    def adam_powers(self, net: int):
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.lib.wgan_get_adam_powers(self._h, net, C.byref(a), C.byref(b)), "get_adam_powers")
+        return a.value, b.value
+
+    def set_adam_powers(self, net: int, b1p: float, b2p: float):
+        self._ck(self.lib.wgan_set_adam_powers(self._h, net, b1p, b2p), "set_adam_powers")
+
+    def init_params(self, seed: int = 0):
+        """tf.layers.dense defaults: Glorot-uniform kernels, zero biases [W:65-80,107-122]."""
+        rng = np.random.default_rng(seed)
+        for name in PARAM_NAMES:
+            _, _, rows, cols, _, _ = self.info[name]
+            if name.endswith("kernel"):
+                lim = np.sqrt(6.0 / (rows + cols))
+                self.set_tensor(name, rng.uniform(-lim, lim, size=(rows, cols)))
+            else:
+                self.set_tensor(name, np.zeros((rows, cols)))
+
+    def state_dict(self) -> dict:
+        """Everything tf.train.Saver would save [W:171]: variables, Adam slots, beta powers."""
+        sd = {"config": dataclasses.asdict(self.cfg)}
+        for kind in ("param", "m", "v"):
+            sd[kind] = {k: self.get_tensor(k, kind) for k in PARAM_NAMES}
+        sd["beta_powers"] = {"generator": self.adam_powers(NET_GENERATOR), "critic": self.adam_powers(NET_CRITIC)}
+        return sd
+
+    def load_state_dict(self, sd: dict):
+        for kind in ("param", "m", "v"):
+            for k, v in sd[kind].items():
+                self.set_tensor(k, v, kind)
+        self.set_adam_powers(NET_GENERATOR, *sd["beta_powers"]["generator"])
+        self.set_adam_powers(NET_CRITIC, *sd["beta_powers"]["critic"])
+
+    # ------------------------------------------------------------------ steps
+    def _mat(self, t: torch.Tensor, cols: int):
+        assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == cols, \
+            f"expected a cuda float32 [rows, {cols}] tensor, got {tuple(t.shape)} {t.dtype} {t.device}"
+        assert t.stride(1) == 1
+        return C.c_void_p(t.data_ptr()), int(t.stride(0)), int(t.shape[0])
+
+    def _allreduce(self, net: int):
+        if self.world > 1:
+            self.dist.all_reduce(self._grad_arena[net], op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def scalars(self, net: int) -> np.ndarray:
+        out = np.empty(4, np.float32)
+        self._ck(self.lib.wgan_get_scalars(self._h, net, out.ctypes.data_as(C.c_void_p), _stream()), "get_scalars")
+        return out
+
+    def critic_step(self, x, z, eps=None, apply: bool = True, read: bool = True):
+        """One critic update [W:199]: gradients of obj_d (+GP), all-reduce, Adam.
+        x [rows, gex], z [rows, noise], eps [rows] are this rank's shard."""
+        xp, ldx, rows = self._mat(x, self.cfg.gex_size)
+        zp, ldz, rz = self._mat(z, self.cfg.noise_input_size)
+        assert rz == rows
+        ep = C.c_void_p(eps.data_ptr()) if eps is not None else C.c_void_p()
+        if eps is not None:
+            assert eps.is_cuda and eps.dtype == torch.float32 and eps.numel() == rows and eps.is_contiguous()
+        self._ck(self.lib.wgan_critic_grads(self._h, xp, ldx, zp, ldz, ep, rows, rows * self.world, _stream()),
+                 "critic_grads")
+        self._allreduce(NET_CRITIC)
+        if apply:
+            self._ck(self.lib.wgan_critic_apply(self._h, _stream()), "critic_apply")
+        if not read:
+            return None
+        s = self.scalars(NET_CRITIC)
+        wass = float(s[0] - s[1])                                       # obj_d [W:137]
+        return {"wasserstein": wass, "gp": float(s[2]), "critic_loss": wass + float(s[2])}
+
+    def generator_step(self, z, apply: bool = True, read: bool = True):
+        """One generator update [W:196]: gradients of obj_g through the critic, all-reduce, Adam."""
+        zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
+        self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, rows * self.world, _stream()),
+                 "generator_grads")
+        self._allreduce(NET_GENERATOR)
+        if apply:
+            self._ck(self.lib.wgan_generator_apply(self._h, _stream()), "generator_apply")
+        if not read:
+            return None
+        return {"gen_loss": -float(self.scalars(NET_GENERATOR)[0])}     # obj_g [W:138]
+
+    def train_iteration(self, x, z, eps=None, read: bool = True):
+        """Reference-literal iteration [W:188-199]: generator update, then critic update, on the
+        same batch and noise (the critic step sees the updated generator)."""
+        g = self.generator_step(z, read=read)
+        c = self.critic_step(x, z, eps, read=read)
+        return {**g, **c} if read else None
+
+    # ------------------------------------------------------------------ model functions
+    def generator(self, z, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """G(z) [W:61-83]: [rows, noise] -> [rows, gex]; batched (any rows <= max_batch)."""
+        zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
+        if out is None:
+            out = torch.empty((rows, self.Gl), device=z.device, dtype=torch.float32)[:, :self.cfg.gex_size]
+        op, ldo, ro = self._mat(out, self.cfg.gex_size)
+        assert ro == rows
+        self._ck(self.lib.wgan_sample(self._h, zp, ldz, op, ldo, rows, _stream()), "sample")
+        return out
+
+    def noise_prior(self, batch_size: int, dim: Optional[int] = None, seed: int = 0, call_id: Optional[int] = None,
+                    row0: Optional[int] = None, data_max_value: float = 1.0) -> torch.Tensor:
+        """abs(Normal(0, data_max/10) + Poisson(1)) [W:91-94], drawn on the device (Philox)."""
+        dim = self.cfg.noise_input_size if dim is None else dim
+        if call_id is None:
+            call_id = self._calls
+            self._calls += 1
+        if row0 is None:
+            row0 = self.rank * batch_size
+        out = torch.empty((batch_size, dim), device=f"cuda:{self.device}", dtype=torch.float32)
+        rc = self.lib.wgan_rng_noise_prior(C.c_void_p(out.data_ptr()), dim, row0, batch_size, dim,
+                                           data_max_value / 10.0, seed, call_id, _stream())
+        if rc != 0:
+            raise _lib.WganError("rng_noise_prior: " + self.lib.wgan_last_error(None).decode())
+        return out
+
+    def uniform(self, rows: int, seed: int, call_id: int, row0: Optional[int] = None) -> torch.Tensor:
+        out = torch.empty((rows,), device=f"cuda:{self.device}", dtype=torch.float32)
+        row0 = self.rank * rows if row0 is None else row0
+        rc = self.lib.wgan_rng_uniform(C.c_void_p(out.data_ptr()), row0, rows, seed, call_id, _stream())
+        if rc != 0:
+            raise _lib.WganError("rng_uniform: " + self.lib.wgan_last_error(None).decode())
+        return out
+
+    def indices(self, rows: int, n_cells: int, seed: int, call_id: int, row0: Optional[int] = None) -> torch.Tensor:
+        out = torch.empty((rows,), device=f"cuda:{self.device}", dtype=torch.int64)
+        row0 = self.rank * rows if row0 is None else row0
+        rc = self.lib.wgan_rng_indices(C.c_void_p(out.data_ptr()), row0, rows, n_cells, seed, call_id, _stream())
+        if rc != 0:
+            raise _lib.WganError("rng_indices: " + self.lib.wgan_last_error(None).decode())
+        return out
+
+    # ------------------------------------------------------------------ resident-data training
+    def set_data(self, cells_by_genes: torch.Tensor):
+        """Keep the (already min-max scaled) training matrix resident, cells-major, padded rows
+        (the reference keeps it genes-major on the host and gathers columns every step [W:188-191])."""
+        n, g = cells_by_genes.shape
+        assert g == self.cfg.gex_size
+        buf = torch.zeros((n, self.Gl), device=f"cuda:{self.device}", dtype=torch.float32)
+        buf[:, :g] = cells_by_genes.to(buf.device, torch.float32)
+        self._data = buf
+        self._xbuf = torch.zeros((self.max_batch, self.Gl), device=buf.device, dtype=torch.float32)
+
+    def gather(self, idx: torch.Tensor) -> torch.Tensor:
+        rows = idx.numel()
+        out = self._xbuf[:rows]
+        rc = self.lib.wgan_gather_rows(C.c_void_p(self._data.data_ptr()), self.Gl, C.c_void_p(idx.data_ptr()),
+                                       C.c_void_p(out.data_ptr()), self.Gl, rows, self.cfg.gex_size, _stream())
+        if rc != 0:
+            raise _lib.WganError("gather_rows: " + self.lib.wgan_last_error(None).decode())
+        return out[:, :self.cfg.gex_size]
+
+    def train_iteration_resident(self, it: int, batch: int, seed: int = 0, read: bool = False):
+        """One WGAN-GP iteration with everything drawn on the device: n_critic critic updates
+        (fresh minibatch, noise and epsilon each) and one generator update (canonical order),
+        or the reference-literal order when cfg.step_order == 'gen_first'."""
+        cfg = self.cfg
+        n = self._data.shape[0]
+        base = it * (cfg.n_critic + 1)
+        out = {}
+        if cfg.step_order == "gen_first":
+            z = self.noise_prior(batch, seed=seed, call_id=base)
+            x = self.gather(self.indices(batch, n, seed, base))
+            eps = self.uniform(batch, seed, base) if cfg.lambda_gp != 0 else None
+            return self.train_iteration(x, z, eps, read=read)
+        for k in range(cfg.n_critic):
+            cid = base + k
+            z = self.noise_prior(batch, seed=seed, call_id=cid)
+            x = self.gather(self.indices(batch, n, seed, cid))
+            eps = self.uniform(batch, seed, cid) if cfg.lambda_gp != 0 else None
+            r = self.critic_step(x, z, eps, read=read)
+            if read:
+                out.update(r)
+        z = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic)
+        r = self.generator_step(z, read=read)
+        if read:
+            out.update(r)
+        return out if read else None
+
+    # ------------------------------------------------------------------ latent fit
+    def latent_fit(self, x: torch.Tensor, steps: int, learn_rate: float = 1e-2, seed: int = 0,
+                   z0: Optional[torch.Tensor] = None):
+        """min_z sum_g (G(z) - x)^2 per cell with G frozen, TF-Adam on z.  Returns (z, loss)."""
+        xp, ldx, rows = self._mat(x, self.cfg.gex_size)
+        Z = self.cfg.noise_input_size
+        z = (z0.clone() if z0 is not None else self.noise_prior(rows, seed=seed, call_id=0x7FFF0000)).contiguous()
+        m = torch.zeros_like(z)
+        v = torch.zeros_like(z)
+        pw = torch.tensor([self.cfg.beta1, self.cfg.beta2, 0, 0], device=z.device, dtype=torch.float32)
+        loss = torch.empty((rows,), device=z.device, dtype=torch.float32)
+        for _ in range(steps):
+            self._ck(self.lib.wgan_latent_fit_step(self._h, C.c_void_p(z.data_ptr()), C.c_void_p(m.data_ptr()),
+                                                   C.c_void_p(v.data_ptr()), C.c_void_p(pw.data_ptr()), xp, ldx,
+                                                   C.c_void_p(loss.data_ptr()), rows, learn_rate, _stream()),
+                     "latent_fit_step")
+        return z, loss
+
+
+def generator(trainer: WGANTrainer, z, reuse: bool = False):
+    """Functional alias with the reference signature generator(z, reuse) [W:61]."""
+    return trainer.generator(z)

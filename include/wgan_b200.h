@@ -1,0 +1,139 @@
+/* wgan_b200.h — C ABI of the B200-native WGAN(-GP) hot path.
+ *
+ * Drop-in boundary for the hot path of scripts/WGAN-GP_minimal.py.  The reference has no
+ * FFI/plugin interface (the path is inlined in a TF1 script); each entry point below cites
+ * the reference lines whose work it replaces:
+ *   [W:n] = scripts/WGAN-GP_minimal.py:n      [A:n] = scripts/Adam_prediction.py:n
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a
+ * negative code on failure (message via wgan_last_error); no exceptions cross the ABI;
+ * step calls are asynchronous on the caller's CUDA stream and never synchronise the host;
+ * the caller owns every buffer it passes in; the handle owns parameters, Adam state and
+ * workspace; a handle is bound to one GPU and is not thread-safe.
+ * All matrices are row-major FP32, one cell (sample) per row, `ld*` = leading dimension
+ * in floats.  GEMMs run as TF32 tcgen05 tensor-core kernels (gemm_mode 0) or as FP32
+ * CUDA-core kernels (gemm_mode 1, verification only).
+ */
+#ifndef WGAN_B200_H
+#define WGAN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wgan_handle wgan_handle;
+typedef void* wgan_stream_t; /* cudaStream_t */
+
+/* Module-level constants of the reference script [W:9-24] plus the build-defined
+ * gradient-penalty knobs (lambda_gp = 0, n_critic = 1 is reference-literal). */
+typedef struct wgan_config {
+  int32_t noise_input_size;   /* [W:13] 100  */
+  int32_t inflate_to_size;    /* [W:14] 600  */
+  int32_t gex_size;           /* [W:15] 6605 */
+  int32_t disc_internal_size; /* [W:17] 200  */
+  int32_t max_batch;          /* largest per-GPU batch (rows) any call will use */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t gemm_mode;          /* 0 = TF32 tcgen05, 1 = FP32 CUDA cores (verification) */
+  int32_t reserved0;
+  float learn_rate;           /* [W:22] 1e-5 */
+  float beta1;                /* [W:154-155] 0.9 */
+  float beta2;                /* [W:154-155] 0.999 */
+  float epsilon;              /* [A:38] 1e-8 */
+  float alpha;                /* tf.nn.leaky_relu default 0.2 [W:69] */
+  float lambda_gp;            /* 0 => no penalty term (reference-literal [W:137]) */
+  float reserved1;
+  float reserved2;
+} wgan_config;
+
+enum { WGAN_NET_GENERATOR = 0, WGAN_NET_CRITIC = 1 };
+enum { WGAN_KIND_PARAM = 0, WGAN_KIND_GRAD = 1, WGAN_KIND_M = 2, WGAN_KIND_V = 3 };
+/* Scalars in the tail of each net's gradient arena (globally summed by the DP all-reduce). */
+enum { WGAN_S_DFAKE = 0, WGAN_S_DREAL = 1, WGAN_S_GP = 2, WGAN_S_SPARE = 3 };
+
+typedef struct wgan_tensor_info {
+  char name[64];   /* TF variable name, e.g. "discriminator/disc_dense1/kernel" [W:63-122] */
+  int32_t net;     /* WGAN_NET_* */
+  int32_t rows;    /* kernel: in, bias: 1 */
+  int32_t cols;    /* kernel: out, bias: out */
+  int32_t ld;      /* device leading dimension (floats) */
+  int64_t offset;  /* float offset inside the net's arena */
+} wgan_tensor_info;
+
+/* ---- lifecycle (replaces graph construction + tf.Session [W:59-172]) ---- */
+int wgan_create(const wgan_config* cfg, wgan_handle** out);
+void wgan_destroy(wgan_handle* h);
+const char* wgan_last_error(const wgan_handle* h); /* h may be NULL: last create error */
+
+/* ---- state I/O in TF variable order [W:140-142]: 12 tensors, generator first ---- */
+int wgan_tensor_count(void);
+int wgan_get_tensor_info(const wgan_handle* h, int index, wgan_tensor_info* out);
+/* Host <-> device copies of one tensor in its logical (unpadded) shape; synchronous. */
+int wgan_get_tensor(wgan_handle* h, int kind, int index, float* host_dst);
+int wgan_set_tensor(wgan_handle* h, int kind, int index, const float* host_src);
+/* beta1_power / beta2_power of one optimizer [A:123-128]; synchronous. */
+int wgan_get_adam_powers(wgan_handle* h, int net, float* beta1_power, float* beta2_power);
+int wgan_set_adam_powers(wgan_handle* h, int net, float beta1_power, float beta2_power);
+/* Flat device arena of one net (for the data-parallel gradient all-reduce and checkpoints).
+ * n_floats includes a 4-float scalar tail (WGAN_S_*) in the GRAD arena. */
+int wgan_get_arena(wgan_handle* h, int net, int kind, float** dev_ptr, size_t* n_floats);
+/* Copies the 4 scalars of a net's grad arena to the host; synchronises `stream`. */
+int wgan_get_scalars(wgan_handle* h, int net, float* host4, wgan_stream_t stream);
+
+/* ---- training steps ---- */
+/* Critic gradients: d(obj_d [+ GP])/d(d_params), generator constant  [W:137,141,154].
+ * x [rows, gex] real cells, z [rows, noise] latent, eps [rows] interpolation weights
+ * (ignored when lambda_gp == 0).  global_batch = total rows over all data-parallel ranks
+ * (the 1/B of the means).  Fills the critic GRAD arena + scalars
+ * {mean-part D_fake, mean-part D_real, GP}.  */
+int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
+                      const float* eps_dev, int rows, int global_batch, wgan_stream_t stream);
+/* Adam update of the critic from its GRAD arena [A:140-151], then beta powers [A:214-225]. */
+int wgan_critic_apply(wgan_handle* h, wgan_stream_t stream);
+/* Generator gradients: d(obj_g)/d(g_params) through the critic [W:138,142,155];
+ * scalar WGAN_S_DFAKE = mean-part of D(G(z)) (obj_g = -that). */
+int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, int global_batch,
+                         wgan_stream_t stream);
+int wgan_generator_apply(wgan_handle* h, wgan_stream_t stream);
+
+/* ---- sampling: G(z) for a batch of cells (replaces the batch-1 loop [W:217-221]) ---- */
+int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int ld_out, int rows,
+                wgan_stream_t stream);
+
+/* ---- latent-vector fit (build-defined): one Adam step on z minimising
+ *      sum_g (G(z) - x)^2 per cell with G frozen.  z_dev [rows, noise] (ld = noise) is
+ *      updated in place; m_dev/v_dev same shape; powers_dev = {beta1_power, beta2_power};
+ *      loss_dev [rows] receives the per-cell loss before the update. ---- */
+int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_dev, float* powers_dev,
+                         const float* x_dev, int ldx, float* loss_dev, int rows, float learn_rate,
+                         wgan_stream_t stream);
+
+/* ---- device input pipeline (replaces host NumPy [W:91-94,188-193]); Philox4x32-10 ---- */
+int wgan_rng_noise_prior(float* out_dev, int ld, int64_t row0, int rows, int dim, float sigma,
+                         uint64_t seed, uint32_t call_id, wgan_stream_t stream);
+int wgan_rng_uniform(float* out_dev, int64_t row0, int rows, uint64_t seed, uint32_t call_id,
+                     wgan_stream_t stream);
+int wgan_rng_indices(int64_t* out_dev, int64_t row0, int rows, uint32_t n_cells, uint64_t seed,
+                     uint32_t call_id, wgan_stream_t stream);
+int wgan_gather_rows(const float* data_dev, int ld_data, const int64_t* idx_dev, float* out_dev,
+                     int ld_out, int rows, int cols, wgan_stream_t stream);
+
+/* ---- introspection / test hooks ---- */
+/* D[M,N] = epi(A * B^T-ish): a_mn / b_mn select MN-major operands (see csrc/gemm_sm100.cuh).
+ * act: 0 none, 1 LeakyReLU(alpha).  Any of bias/aux/row_scale/row_sumsq may be NULL.
+ * force_splits <= 0 lets the engine pick.  *sumsq_tiles receives the number of row_sumsq tiles. */
+int wgan_gemm(wgan_handle* h, int a_mn, int b_mn, const float* A, int lda, const float* B, int ldb,
+              float* D, int ldd, int M, int N, int K, const float* bias, int act, const float* aux,
+              int ld_aux, const float* row_scale, float* row_sumsq, int* sumsq_tiles,
+              int force_splits, wgan_stream_t stream);
+/* Named internal buffers ("norms", "gx", "x_tilde", ...) for parity tests; NULL if unknown. */
+int wgan_get_buffer(wgan_handle* h, const char* name, float** dev_ptr, int* rows, int* cols, int* ld);
+/* Number of kernels launched by this handle since creation (bench's gpu_launches). */
+int64_t wgan_launch_count(const wgan_handle* h);
+int wgan_padded_ld(int cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WGAN_B200_H */

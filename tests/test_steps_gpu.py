@@ -1,0 +1,158 @@
+"""Step-level GPU parity against the CPU oracle (oracle/wgan_oracle.py, fp64): losses, gradient
+penalty, every parameter gradient, post-Adam parameters / m / v, sampling, RNG, multi-step drift.
+
+Tolerances (normalised max error, err = max|got-ref| / max|ref| per tensor):
+  TF32 tensor-core mode (gemm_mode 0): 5e-3 on gradients, 2e-3 on scalars (north-star: 1e-3 class;
+  K = 6605 reductions of TF32-rounded operands measured ~1e-4..1e-3)
+  FP32 verification mode (gemm_mode 1): 1e-4 on gradients, 2e-5 on scalars.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import wgan_oracle as O  # noqa: E402
+
+GTOL = {0: 5e-3, 1: 1e-4}
+STOL = {0: 2e-3, 1: 2e-5}
+
+SMALL = dict(noise_input_size=20, inflate_to_size=40, gex_size=133, disc_internal_size=24)
+REF = dict(noise_input_size=100, inflate_to_size=600, gex_size=6605, disc_internal_size=200)
+
+
+def _setup(dims, B, lam, mode, seed=0):
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer
+    cfg = WGANConfig(lambda_gp=lam, **dims)
+    ocfg = O.OracleConfig(lambda_gp=lam, **dims)
+    tr = WGANTrainer(cfg, max_batch=B, device=0, gemm_mode=mode)
+    P = O.random_params(ocfg, seed=seed + 1, dtype=np.float64)
+    tr.set_params(P)
+    rng = np.random.default_rng(seed)
+    x = rng.random((B, cfg.gex_size)) * (rng.random((B, cfg.gex_size)) > 0.5)
+    z = np.abs(rng.normal(0, 0.1, (B, cfg.noise_input_size)) + rng.poisson(1.0, (B, cfg.noise_input_size)))
+    eps = rng.random(B)
+    # the device sees float32 inputs; give the oracle the same rounded values
+    x, z, eps = (a.astype(np.float32).astype(np.float64) for a in (x, z, eps))
+    P = {k: v.astype(np.float32).astype(np.float64) for k, v in P.items()}
+    dev = torch.device("cuda:0")
+    xd, zd, ed = (torch.tensor(a, dtype=torch.float32, device=dev) for a in (x, z, eps))
+    return tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed)
+
+
+def _relerr(got, ref):
+    ref = np.asarray(ref, np.float64).reshape(got.shape)
+    return float(np.abs(got - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("dims,B", [(SMALL, 48), (SMALL, 7), (REF, 32), (REF, 200)])
+@pytest.mark.parametrize("lam", [0.0, 10.0])
+def test_critic_step_grads(dims, B, lam, mode):
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(dims, B, lam, mode)
+    s = tr.critic_step(xd, zd, ed, apply=False)
+    so, go = O.critic_step_grads(P, x, z, eps, ocfg)
+    for k in ("wasserstein", "gp", "critic_loss"):
+        assert abs(s[k] - so[k]) <= STOL[mode] * (abs(so[k]) + 1e-2), (k, s, so)
+    g = tr.get_grads(O.CRITIC_NAMES)
+    for k in O.CRITIC_NAMES:
+        if np.abs(go[k]).max() == 0:
+            assert np.abs(g[k]).max() == 0, k
+        else:
+            assert _relerr(g[k], go[k]) < GTOL[mode], (k, _relerr(g[k], go[k]))
+    if lam:
+        _, _, n = O.gradient_penalty(P, x, O.generator_forward(P, z)[2], eps, lam)
+        got_n = tr.buffer("norms").cpu().numpy()[0]
+        assert _relerr(got_n, n) < STOL[mode]
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("dims,B", [(SMALL, 48), (REF, 32), (REF, 200)])
+def test_generator_step_grads(dims, B, mode):
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(dims, B, 0.0, mode)
+    s = tr.generator_step(zd, apply=False)
+    so, go = O.generator_step_grads(P, z, ocfg)
+    assert abs(s["gen_loss"] - so["gen_loss"]) <= STOL[mode] * (abs(so["gen_loss"]) + 1e-2)
+    g = tr.get_grads(O.GEN_NAMES)
+    for k in O.GEN_NAMES:
+        assert _relerr(g[k], go[k]) < GTOL[mode], (k, _relerr(g[k], go[k]))
+
+
+def test_adam_bit_exact_given_gradient():
+    """TF-Adam [A:140-151,214-225]: with the device's own gradient fed to the fp32 oracle update,
+    params / m / v / beta powers must match bit for bit over several steps."""
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(SMALL, 16, 10.0, 1)
+    P32 = {k: v.astype(np.float32) for k, v in P.items()}
+    opt = O.OracleAdam(O.CRITIC_NAMES, P32, ocfg)
+    for step in range(4):
+        tr.critic_step(xd, zd, ed, apply=False, read=False)
+        g = {k: tr.get_tensor(k, "grad").reshape(P32[k].shape) for k in O.CRITIC_NAMES}
+        tr._ck(tr.lib.wgan_critic_apply(tr._h, None), "critic_apply")
+        opt.apply(P32, g)
+        for k in O.CRITIC_NAMES:
+            assert np.array_equal(tr.get_tensor(k).reshape(P32[k].shape), P32[k]), (step, k)
+            assert np.array_equal(tr.get_tensor(k, "m").reshape(P32[k].shape), opt.m[k]), (step, k)
+            assert np.array_equal(tr.get_tensor(k, "v").reshape(P32[k].shape), opt.v[k]), (step, k)
+        b1p, b2p = tr.adam_powers(1)
+        assert np.float32(b1p) == opt.beta1_power and np.float32(b2p) == opt.beta2_power
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_reference_literal_iterations_drift(mode):
+    """[W:188-199]: generator update then critic update on the same batch, 5 iterations from the
+    same weights; device vs fp64 oracle loss curves and final parameters."""
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(SMALL, 32, 0.0, mode)
+    ocfg.learn_rate = 1e-3
+    tr.close()
+    from arshamg_scrnaseq_wgan_b200 import WGANTrainer
+    tr = WGANTrainer(WGANConfig.reference_literal(learn_rate=1e-3, **SMALL), max_batch=32, device=0, gemm_mode=mode)
+    tr.set_params(P)
+    ot = O.OracleTrainer(ocfg, P)
+    for it in range(5):
+        s = tr.train_iteration(xd, zd)
+        so = ot.reference_iteration(x, z)
+        assert abs(s["gen_loss"] - so["gen_loss"]) <= STOL[mode] * (abs(so["gen_loss"]) + 1e-2), it
+        assert abs(s["wasserstein"] - so["wasserstein"]) <= 5 * STOL[mode] * (abs(so["wasserstein"]) + 1e-2), it
+    for k in O.PARAM_NAMES:
+        assert _relerr(tr.get_tensor(k).reshape(ot.P[k].shape), ot.P[k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_sampler(mode):
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(REF, 100, 0.0, mode)
+    cells = tr.generator(zd).cpu().numpy()
+    ref = O.generator_forward(P, z)[2]
+    assert cells.shape == (100, 6605)
+    assert _relerr(cells, ref) < STOL[mode]
+    # unpadded, unaligned destination
+    out = torch.empty((100 * 6605 + 1,), device="cuda:0")[1:].view(100, 6605)
+    tr.generator(zd, out=out)
+    assert _relerr(out.cpu().numpy(), ref) < STOL[mode]
+
+
+def test_rng_matches_oracle():
+    tr, *_ = _setup(SMALL, 8, 0.0, 1)
+    zn = tr.noise_prior(37, 20, seed=1234, call_id=5, row0=11).cpu().numpy()
+    ref = O.rng_noise_prior(1234, 5, 11, 37, 20, 0.1)
+    assert np.abs(zn - ref).max() < 1e-5          # logf / cosf differ by ulps between libm and CUDA
+    u = tr.uniform(1000, seed=99, call_id=3, row0=5).cpu().numpy()
+    assert np.array_equal(u, O.rng_uniform(99, 3, 5, 1000))
+    idx = tr.indices(1000, 1500, seed=99, call_id=3, row0=5).cpu().numpy()
+    assert np.array_equal(idx, O.rng_indices(99, 3, 5, 1000, 1500))
+    assert idx.min() >= 0 and idx.max() < 1500
+
+
+def test_latent_fit_matches_oracle():
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(SMALL, 16, 0.0, 1)
+    target = O.generator_forward(P, np.abs(z[::-1]))[2]
+    td = torch.tensor(target, dtype=torch.float32, device="cuda:0")
+    z1, loss = tr.latent_fit(td, steps=1, learn_rate=1e-2, z0=zd)
+    lo, dz = O.latent_fit_grads(P, z, target)
+    assert _relerr(loss.cpu().numpy(), lo) < 1e-4
+    # one TF-Adam step from zero state moves every coordinate by lr * sign(dz) (up to eps)
+    step = (zd - z1).cpu().numpy()
+    mask = np.abs(dz) > 1e-3
+    assert np.allclose(step[mask], 1e-2 * np.sign(dz[mask]), rtol=1e-3, atol=1e-6)
+    z2, loss2 = tr.latent_fit(td, steps=200, learn_rate=1e-2, z0=zd)
+    assert float(loss2.mean()) < float(loss.mean())
