@@ -130,7 +130,7 @@ int post_launch(wgan_handle* h, const char* what) {
 // Tensor maps
 // ------------------------------------------------------------------------------------------
 int make_map_2d(wgan_handle* h, CUtensorMap* m, const float* ptr, uint64_t inner, uint64_t outer,
-                uint64_t ld_floats, uint32_t box_inner, uint32_t box_outer, bool tf32) {
+                uint64_t ld_floats, uint32_t box_inner, uint32_t box_outer, bool mn_major) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld_floats & 3) != 0)
     FAIL("TMA operand must be 16-byte aligned with ld %% 4 == 0 (ptr=%p ld=%llu)", (const void*)ptr,
          (unsigned long long)ld_floats);
@@ -138,10 +138,12 @@ int make_map_2d(wgan_handle* h, CUtensorMap* m, const float* ptr, uint64_t inner
   cuuint64_t strides[1] = {ld_floats * 4};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = h->encode(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                         const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // operands are read as TF32 (round-to-nearest on load); MN-major 32-bit operands must use the
+  // 32-byte-atom flavour of the 128 B swizzle (see make_smem_desc in gemm_sm100.cuh)
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(2d) failed with %d", (int)r);
   return 0;
 }
@@ -262,9 +264,9 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     const Part& pt = parts[i];
     GemmParams p;
     memset(&p, 0, sizeof p);
-    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, BM, true));
+    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, BM, false));
     else       TRY(make_map_2d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, 32, 32, true));
-    if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, bn, true));
+    if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, bn, false));
     else       TRY(make_map_2d(h, &p.tma_b, pt.B, N, pt.K, pt.ldb, 32, 32, true));
     TRY(make_map_out(h, &p.tma_d, out + (direct ? 0 : slab * slab0), N, M, splits[i], ldd, slab));
     p.M = M; p.N = N; p.K = pt.K;
@@ -274,11 +276,10 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     p.m_tiles = m_tiles; p.n_tiles = n_tiles;
     p.stages = stages;
     p.total_kb = cdiv(pt.K, BK);
+    // partials that go to the workspace stay raw (p.epi is all-zero) even when this part has a
+    // single split; finish_splitk_kernel applies the epilogue after summing the slabs
     if (direct) p.epi = epi;
-    else { p.epi.act = 0; p.splits = splits[i]; }
-    // when the partials go to the workspace the fused epilogue must stay off even for 1 split
-    const bool raw_single = (!direct && splits[i] == 1);
-    if (raw_single) { memset(&p.epi, 0, sizeof p.epi); }
+    else p.splits = splits[i];
     int grid = tiles * splits[i];
     if (grid > h->num_sms) grid = h->num_sms;
     if (!a_mn && b_mn) TRY((launch_tc<false, true>(h, p, smem, grid, s)));
@@ -439,7 +440,6 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
     return fail("cuTensorMapEncodeTiled entry point not available");
   h->encode = reinterpret_cast<EncodeTiledFn>(fn);
 
-  if (cudaMemcpyToSymbol(c_poisson1_cdf, nullptr, 0) != cudaSuccess) { /* symbol touch; real upload below */ }
   {
     float cdf[12];
     double acc = 0.0, term = exp(-1.0);

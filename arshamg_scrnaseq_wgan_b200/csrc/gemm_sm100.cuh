@@ -150,18 +150,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor (SWIZZLE_128B, descriptor version 1 = Blackwell).
-//   K-major : rows of 128 B (32 tf32 of K), 8-row swizzle atoms 1024 B apart (SBO); LBO unused.
-//   MN-major: a [32 k-rows][32 mn] box per 32 MN elements; boxes 4096 B apart (LBO), the 8-k-row
-//             atoms inside a box 1024 B apart (SBO).
+// Shared-memory matrix descriptor (descriptor version 1 = Blackwell).
+//   K-major : SWIZZLE_128B (layout type 2): rows of 128 B (32 tf32 of K), 8-row swizzle atoms
+//             1024 B apart (SBO); LBO unused.
+//   MN-major: 32-bit operands only support SWIZZLE_128B_BASE32B (layout type 1, TMA swizzle
+//             128B_ATOM_32B: 32 B chunks XOR-ed with k-row % 4): a [32 k-rows][32 mn] box per 32 MN
+//             elements; boxes 4096 B apart (LBO), the 4-k-row atoms inside a box 512 B apart (SBO).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((addr >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;          // descriptor version (sm_100)
-  d |= 2ull << 61;          // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 
@@ -283,10 +285,10 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int s = 0; s < BK / UMMA_K; ++s) {
-            const uint64_t adesc = A_MN ? make_smem_desc(sa + s * 1024, 4096, 1024)
-                                        : make_smem_desc(sa + s * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(sb + s * 1024, 4096, 1024)
-                                        : make_smem_desc(sb + s * 32, 16, 1024);
+            const uint64_t adesc = A_MN ? make_smem_desc(sa + s * 1024, 4096, 512, 1)
+                                        : make_smem_desc(sa + s * 32, 16, 1024, 2);
+            const uint64_t bdesc = B_MN ? make_smem_desc(sb + s * 1024, 4096, 512, 1)
+                                        : make_smem_desc(sb + s * 32, 16, 1024, 2);
             umma_tf32(d_tmem, adesc, bdesc, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar + 8 * stage);      // frees the smem slot when these MMAs retire
