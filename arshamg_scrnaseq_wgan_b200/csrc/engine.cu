@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,7 @@ using namespace wg;
 namespace {
 
 thread_local std::string g_create_error;
+std::atomic<long long> g_pipeline_launches{0};   // launches of the handle-less input-pipeline kernels
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -208,14 +210,17 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
 
   if (h->cfg.gemm_mode == 1) {
     // FP32 CUDA-core verification path: raw products into slabs, then the shared finish kernel.
-    float* raw = (nparts == 1) ? D : h->splitws;
-    if (nparts > 1 && slab * nparts > h->splitws_n) FAIL("gemm: split workspace too small");
+    // raw products go through the workspace so that an epilogue operand aliasing D (in-place
+    // slope mask) is still intact when the finish kernel reads it
+    const bool ws_fits = slab * nparts <= h->splitws_n;
+    if (!ws_fits && (nparts > 1 || epi.aux == D)) FAIL("gemm: split workspace too small");
+    float* raw = ws_fits ? h->splitws : D;
     for (int i = 0; i < nparts; ++i) {
       const Part& pt = parts[i];
       dim3 grid(cdiv(N, 64), cdiv(M, 64));
       gemm_fp32_kernel<<<grid, 256, 0, s>>>(pt.A, a_mn ? 1 : pt.lda, a_mn ? pt.lda : 1, pt.B,
                                             b_mn ? 1 : pt.ldb, b_mn ? pt.ldb : 1,
-                                            raw + (nparts == 1 ? 0 : slab * i), ldd, M, N, pt.K);
+                                            raw + slab * i, ldd, M, N, pt.K);
       TRY(post_launch(h, "gemm_fp32_kernel"));
     }
     finish_splitk_kernel<<<ew_grid(static_cast<size_t>(M) * 32, 256, h->num_sms), 256, 0, s>>>(
@@ -392,7 +397,9 @@ int wgan_padded_ld(int cols) { return cols == 1 ? 1 : round4(cols); }
 int wgan_tensor_count(void) { return 12; }
 
 const char* wgan_last_error(const wgan_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
-int64_t wgan_launch_count(const wgan_handle* h) { return h ? h->launches : 0; }
+int64_t wgan_launch_count(const wgan_handle* h) {
+  return (h ? h->launches : 0) + static_cast<int64_t>(g_pipeline_launches.load());
+}
 
 void wgan_destroy(wgan_handle* h) {
   if (!h) return;
@@ -801,6 +808,7 @@ int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_de
 static int rng_launch_check(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_create_error = std::string(what) + ": " + cudaGetErrorString(e); return -3; }
+  g_pipeline_launches.fetch_add(1);
   return 0;
 }
 static int upload_poisson_cdf_once() {

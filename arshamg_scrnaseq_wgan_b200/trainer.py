@@ -360,6 +360,51 @@ class WGANTrainer:
             out.update(r)
         return out if read else None
 
+    # ------------------------------------------------------------------ host-fed iteration (e2e)
+    def train_iteration_host(self, xs, zs, epss, z_gen, read: bool = True):
+        """One WGAN-GP iteration fed from HOST float32 buffers, the way the reference feeds
+        ``sess.run`` [W:196,199]: per critic update x [B, gex], z [B, noise], eps [B]; then z_gen for
+        the generator update.  Pinned host tensors are copied on a second stream into two
+        alternating device staging sets so the H2D copy of update k+1 overlaps the kernels of update k.
+        Returns the losses as host floats (device->host read inside the call)."""
+        cfg = self.cfg
+        B = xs[0].shape[0]
+        dev = f"cuda:{self.device}"
+        if getattr(self, "_stage", None) is None or self._stage[0][0].shape[0] != B:
+            self._stage = [(torch.empty((B, cfg.gex_size), device=dev), torch.empty((B, cfg.noise_input_size), device=dev),
+                            torch.empty((B,), device=dev)) for _ in range(2)]
+            self._zgen = torch.empty((B, cfg.noise_input_size), device=dev)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+            self._nfeed = 0
+        main = torch.cuda.current_stream()
+        out = {}
+        n = len(xs)
+        for k in range(n):
+            slot = self._nfeed % 2
+            xd, zd, ed = self._stage[slot]
+            with torch.cuda.stream(self._copy_stream):
+                if self._nfeed >= 2:
+                    self._copy_stream.wait_event(self._free[slot])
+                xd.copy_(xs[k], non_blocking=True)
+                zd.copy_(zs[k], non_blocking=True)
+                if cfg.lambda_gp != 0:
+                    ed.copy_(epss[k], non_blocking=True)
+                if k == n - 1:
+                    self._zgen.copy_(z_gen, non_blocking=True)
+                self._ready[slot].record(self._copy_stream)
+            main.wait_event(self._ready[slot])
+            r = self.critic_step(xd, zd, ed if cfg.lambda_gp != 0 else None, read=read and k == n - 1)
+            self._free[slot].record(main)
+            self._nfeed += 1
+            if r:
+                out.update(r)
+        r = self.generator_step(self._zgen, read=read)
+        if r:
+            out.update(r)
+        return out if read else None
+
     # ------------------------------------------------------------------ latent fit (SURVEY D5)
     def latent_fit(self, x: torch.Tensor, steps: int, learn_rate: float = 1e-2, seed: int = 0,
                    z0: Optional[torch.Tensor] = None):

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the WGAN-GP hot path (BASELINE.json metric: train iters/sec, generated cells/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one WGAN-GP training iteration of BASELINE config 2: reference architecture
+(100-600-600-6605 generator, 6605-200-200-1 critic), per-GPU batch 4096, n_critic = 5 critic
+updates with gradient penalty (lambda = 10) + 1 generator update, TF-Adam; synthetic lTPM-like
+data of the CSV's gene dimension (6605), 1500 resident training cells [W:18].  For N > 1 the
+driver launches one rank per GPU with torchrun; the batch is sharded by rank (weak scaling:
+global batch = 4096 * N, one NCCL all-reduce of the flat gradient arena per optimizer step) and
+`value` counts batch-4096 iterations completed by the whole job per second.
+
+`--impl reference` times the reference's CPU implementation of the same path: TensorFlow 1.x is
+not installable here, so this is the FP32 torch-CPU restatement of the reference graph
+(oracle/wgan_torch_cpu.py) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 4096
+N_CELLS = 1500            # num_cells_train [W:18]
+METRIC = "wgan_gp_train_iters_per_sec"
+UNIT = "iters/s (batch-4096 iterations: 5 critic+GP updates + 1 generator update each)"
+# SURVEY 8d / BASELINE.md section 5: algorithmic work per sample
+FLOP_PER_SAMPLE_ITER = 1.851e8
+FLOP_GEN_FWD = 8.766e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_cells(n_cells, n_genes, seed, device):
+    """log2(TPM+1)-like cells x genes matrix, per-gene min-max scaled to [0,1] as [W:34-39]
+    (per-gene dropout probability and gamma magnitude)."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    p_drop = torch.empty(1, n_genes).uniform_(0.3, 0.95, generator=g)
+    scale = torch.empty(1, n_genes).uniform_(2.0, 12.0, generator=g)
+    expressed = torch.rand(n_cells, n_genes, generator=g) > p_drop
+    mag = torch._standard_gamma(torch.full((n_cells, n_genes), 2.0), generator=g) * (scale / 2.0)
+    raw = torch.where(expressed, mag, torch.zeros(()))
+    lo = raw.min(0, keepdim=True).values
+    rng = raw.max(0, keepdim=True).values - lo
+    rng[rng == 0] = 1.0
+    return ((raw - lo) / rng).to(device=device, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: FP32 torch-CPU restatement of the reference graph
+# ------------------------------------------------------------------------------------------------
+def cpu_iteration_runner(batch, seed=0):
+    import numpy as np
+    import torch
+    from oracle import wgan_oracle as O
+    from oracle.wgan_torch_cpu import TorchCpuTrainer
+    cfg = O.OracleConfig(lambda_gp=10.0, n_critic=5)
+    tr = TorchCpuTrainer(cfg, O.glorot_init(cfg, seed, dtype=np.float32))
+    data = synthetic_cells(N_CELLS, cfg.gex_size, seed, "cpu")
+    g = torch.Generator().manual_seed(seed + 1)
+
+    def noise(b):
+        return (torch.randn(b, cfg.noise_input_size, generator=g) * 0.1 +
+                torch.poisson(torch.ones(b, cfg.noise_input_size), generator=g)).abs()
+
+    def one_iteration():
+        xs, zs, es = [], [], []
+        for _ in range(cfg.n_critic):
+            idx = torch.randint(N_CELLS, (batch,), generator=g)         # [W:188]
+            xs.append(data[idx]); zs.append(noise(batch)); es.append(torch.rand(batch, generator=g))
+        return tr.wgan_gp_iteration(xs, zs, es, noise(batch))
+    return one_iteration
+
+
+def time_cpu(batch, steps, warmup, budget_s):
+    """Times `steps` iterations after `warmup`; if that would exceed budget_s, uses a smaller
+    batch sample and extrapolates linearly in the batch (stated in `sample`)."""
+    import torch
+    run = cpu_iteration_runner(batch)
+    t0 = time.perf_counter(); run(); t_first = time.perf_counter() - t0
+    b = batch
+    while (steps + warmup) * t_first * (b / batch) > budget_s and b > 256:
+        b //= 2
+    if b != batch:
+        run = cpu_iteration_runner(b)
+        run()
+    for _ in range(max(warmup - 1, 0)):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = time.perf_counter() - t0
+    its = steps / dt * (b / batch)
+    sample = (f"{steps} timed WGAN-GP iterations (5 critic+GP + 1 generator update) at batch {b}"
+              + ("" if b == batch else f", scaled by {b}/{batch} to batch-{batch} iterations")
+              + f" after {warmup} warm-up; FP32 torch-CPU restatement of the reference graph (TensorFlow not installable)")
+    return its, dt / steps * 1e3, torch.get_num_threads(), sample, b
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    its, ms, cores, sample, b = time_cpu(args.batch, args.steps, args.warmup, budget_s=200.0)
+    line = {"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: WGAN-GP iteration, reference dims 100-600-600-6605 / 6605-200-200-1, "
+                                   f"batch {args.batch}, n_critic 5, lambda 10, synthetic lTPM 1500x6605"},
+            "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def time_kernel(fn, iters, torch):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def dominant_kernel_roofline(tr, batch, torch, pk):
+    """Times the iteration's heaviest kernel instances in isolation (CUDA events on the launch
+    stream, inputs > L2) and reports the dominant one against its binding roof."""
+    import ctypes as C
+    cfg = tr.cfg
+    G, Gl, Hd, Hg = cfg.gex_size, tr.Gl, cfg.disc_internal_size, cfg.inflate_to_size
+    dev = f"cuda:{tr.device}"
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    null = C.c_void_p()
+    tiles = C.c_int(0)
+    X3 = torch.rand((3 * batch, Gl), device=dev)
+    W1 = torch.rand((G, Hd), device=dev) - 0.5
+    b1 = torch.zeros((Hd,), device=dev)
+    H1 = torch.empty((3 * batch, Hd), device=dev)
+    D1 = torch.rand((3 * batch, Hd), device=dev) - 0.5
+    GW1 = torch.empty((G, Hd), device=dev)
+    GH2 = torch.rand((batch, Hg), device=dev)
+    WG3 = torch.rand((Hg, Gl), device=dev) - 0.5
+    bg3 = torch.zeros((G,), device=dev)
+    XT = torch.empty((batch, Gl), device=dev)
+
+    def gemm(a_mn, b_mn, A, B, D, M, N, K, bias=None, act=0):
+        rc = tr.lib.wgan_gemm(tr._h, a_mn, b_mn, p(A), A.stride(0), p(B), B.stride(0), p(D), D.stride(0), M, N, K,
+                              p(bias) if bias is not None else null, act, null, 0, null, null, C.byref(tiles), 0, st())
+        assert rc == 0, tr.lib.wgan_last_error(tr._h)
+
+    cases = {
+        # name: (fn, flops, algorithmic bytes, launches per iteration of this shape class)
+        "critic layer-1 forward [3B x 6605] x [6605 x 200] (TF32 tcgen05, split-K)":
+            (lambda: gemm(0, 1, X3, W1, H1, 3 * batch, Hd, G, b1, 1), 2.0 * 3 * batch * G * Hd,
+             4.0 * (3 * batch * G + G * Hd + 3 * batch * Hd), 5),
+        "critic layer-1 wgrad [6605 x 3B] x [3B x 200] (TF32 tcgen05, split-K)":
+            (lambda: gemm(1, 1, X3, D1, GW1, G, Hd, 3 * batch), 2.0 * 3 * batch * G * Hd,
+             4.0 * (3 * batch * G + 3 * batch * Hd + G * Hd), 5),
+        "generator output forward [B x 600] x [600 x 6605] (TF32 tcgen05, bias+LeakyReLU epilogue)":
+            (lambda: gemm(0, 1, GH2, WG3, XT, batch, G, Hg, bg3, 1), 2.0 * batch * G * Hg,
+             4.0 * (batch * Hg + Hg * G + batch * G), 6),
+    }
+    out = []
+    for name, (fn, flops, byts, per_iter) in cases.items():
+        ms = time_kernel(fn, 20, torch)
+        out.append({"kernel": name, "ms": ms, "tflops": flops / ms / 1e9, "gbs": byts / ms / 1e6,
+                    "per_iter": per_iter, "flops": flops, "bytes": byts})
+    dom = max(out, key=lambda r: r["ms"] * r["per_iter"])
+    tf32_peak = pk["bf16_burst"] / 2.0
+    t_tensor = dom["flops"] / (tf32_peak * 1e12)
+    t_hbm = dom["bytes"] / (pk["hbm_gbs"] * 1e9)
+    if t_hbm >= t_tensor:
+        roof = {"bound": "hbm", "achieved": dom["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": dom["gbs"] / pk["hbm_gbs"]}
+    else:
+        roof = {"bound": "tensor", "achieved": dom["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": dom["tflops"] / tf32_peak,
+                "peak_note": "TF32 dense = measured bf16 burst / 2 (TF32 not measured separately)"}
+    roof.update({"kernel": dom["kernel"], "ms_per_launch": dom["ms"], "traffic": None, "peak_source": pk["src"],
+                 "algorithmic_flops_per_launch": dom["flops"], "algorithmic_bytes_per_launch": dom["bytes"],
+                 "others": [{k: r[k] for k in ("kernel", "ms", "tflops", "gbs", "per_iter")} for r in out]})
+    return roof
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer, _lib
+    _lib.build()
+    cfg = WGANConfig(lambda_gp=10.0, n_critic=5)
+    B = args.batch
+    tr = WGANTrainer(cfg, max_batch=max(B, 32768), device=local)
+    tr.init_params(seed=0)
+    tr.set_data(synthetic_cells(N_CELLS, cfg.gex_size, 0, f"cuda:{local}"))
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing: `value` ----------------
+    for it in range(args.warmup):
+        tr.train_iteration_resident(it, B, seed=0)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = tr.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for it in range(args.steps):
+        tr.train_iteration_resident(args.warmup + it, B, seed=0)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = tr.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * 1000.0 / ms_step                     # batch-4096 iterations/s over the whole job
+    last = tr.train_iteration_resident(args.warmup + args.steps, B, seed=0, read=True)
+
+    # ---------------- end-to-end through the public API with HOST buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        nb = cfg.n_critic
+        xs = [torch.rand((B, cfg.gex_size)).pin_memory() for _ in range(nb)]
+        zs = [torch.rand((B, cfg.noise_input_size)).abs().pin_memory() for _ in range(nb + 1)]
+        es = [torch.rand((B,)).pin_memory() for _ in range(nb)]
+        h2d = sum(t_.numel() * 4 for t_ in xs + zs + es)
+        for _ in range(max(3, args.warmup // 2)):
+            tr.train_iteration_host(xs, zs[:nb], es, zs[nb])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = tr.train_iteration_host(xs, zs[:nb], es, zs[nb])        # returns host floats (D2H inside)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * args.steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 32, "ms_per_step": float(tt.item()) / args.steps * 1e3,
+               "api": "WGANTrainer.train_iteration_host(x, z, eps, z_gen) with pinned host float32 feeds "
+                      "(x [4096,6605], z [4096,100], eps [4096] per critic update, as the reference's feed_dict "
+                      "[W:196,199]); losses read back every iteration", "last": out}
+
+    # ---------------- sampler: generated cells/sec ----------------
+    SB = 32768
+    zsamp = tr.noise_prior(SB, seed=1, call_id=77)
+    cells = torch.empty((SB, tr.Gl), device=f"cuda:{local}")[:, :cfg.gex_size]
+    ms_s = time_kernel(lambda: tr.generator(zsamp, out=cells), 10, torch)
+    ts = torch.tensor([ms_s], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    cells_per_s = world * SB / (float(ts.item()) * 1e-3)
+    sampler = {"metric": "generated_cells_per_sec", "value": cells_per_s, "unit": "cells/s", "chunk": SB,
+               "ms_per_chunk": float(ts.item()),
+               "tensor_tflops": cells_per_s * FLOP_GEN_FWD / 1e12,
+               "output_gbs": cells_per_s * cfg.gex_size * 4 / 1e9}
+
+    roof = cpu = None
+    if rank == 0:
+        roof = dominant_kernel_roofline(tr, B, torch, pk)
+        if world == 1 and not args.no_cpu_baseline:
+            its, ms, cores, sample, b = time_cpu(B, 2, 1, budget_s=45.0)
+            cpu = {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": "BASELINE config 2: WGAN-GP iteration, reference dims 100-600-600-6605 / "
+                                       f"6605-200-200-1, per-GPU batch {B} (global {B * world}), n_critic 5, lambda 10, "
+                                       "TF-Adam lr 1e-5, synthetic lTPM 1500x6605 resident in HBM, device Philox RNG + gather",
+                           "parallelism": f"dp{world}", "l2": "per-step working set 325 MB > 126 MB L2 (inputs larger than L2)",
+                           "iteration_tflops": world * B * FLOP_PER_SAMPLE_ITER / (ms_step * 1e-3) / 1e12},
+                "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "sampler": sampler, "losses": last}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
