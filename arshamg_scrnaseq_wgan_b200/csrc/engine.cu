@@ -69,6 +69,7 @@ struct wgan_handle {
   // workspace
   float *zbuf, *gh1, *gh2, *xcat, *h1, *h2, *d2, *d1, *dout, *v2, *gd2, *gd1, *dz;
   float *nsq, *crow, *pen, *norms, *colpart, *splitws, *sample_tmp;
+  int colpart_stride;
   size_t splitws_n;
   int nsq_tiles_max;
   int last_gx_rows;
@@ -145,7 +146,7 @@ int make_map_2d(wgan_handle* h, CUtensorMap* m, const float* ptr, uint64_t inner
   CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(2d) failed with %d", (int)r);
   return 0;
 }
@@ -187,6 +188,18 @@ size_t gemm_smem_bytes(int bn, int* stages_out) {
   return need;
 }
 
+int launch_finish(wgan_handle* h, const float* part, size_t slab, int splits, float* D, int ldd, int M, int N,
+                  const EpiParams& epi, cudaStream_t s) {
+  if (epi.row_sumsq == nullptr) {
+    const size_t n = static_cast<size_t>(M) * ((N + 3) / 4);
+    finish_splitk_vec4_kernel<<<ew_grid(n, 256, h->num_sms), 256, 0, s>>>(part, slab, splits, D, ldd, M, N, epi);
+    return post_launch(h, "finish_splitk_vec4_kernel");
+  }
+  finish_splitk_kernel<<<ew_grid(static_cast<size_t>(M) * 32, 256, h->num_sms), 256, 0, s>>>(part, slab, splits, D,
+                                                                                            ldd, M, N, epi);
+  return post_launch(h, "finish_splitk_kernel");
+}
+
 template <bool A_MN, bool B_MN>
 int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int grid, cudaStream_t s) {
   static bool attr_set[16] = {};
@@ -223,9 +236,7 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
                                             raw + slab * i, ldd, M, N, pt.K);
       TRY(post_launch(h, "gemm_fp32_kernel"));
     }
-    finish_splitk_kernel<<<ew_grid(static_cast<size_t>(M) * 32, 256, h->num_sms), 256, 0, s>>>(
-        raw, slab, nparts, D, ldd, M, N, epi);
-    TRY(post_launch(h, "finish_splitk_kernel"));
+    TRY(launch_finish(h, raw, slab, nparts, D, ldd, M, N, epi, s));
     if (sumsq_tiles) *sumsq_tiles = 1;
     return 0;
   }
@@ -294,9 +305,7 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     slab0 += splits[i];
   }
   if (!direct) {
-    finish_splitk_kernel<<<ew_grid(static_cast<size_t>(M) * 32, 256, h->num_sms), 256, 0, s>>>(
-        h->splitws, slab, total_splits, D, ldd, M, N, epi);
-    TRY(post_launch(h, "finish_splitk_kernel"));
+    TRY(launch_finish(h, h->splitws, slab, total_splits, D, ldd, M, N, epi, s));
     if (sumsq_tiles) *sumsq_tiles = 1;
   } else if (sumsq_tiles) {
     *sumsq_tiles = n_tiles;
@@ -327,20 +336,43 @@ int gemm1(wgan_handle* h, bool a_mn, bool b_mn, const float* A, int lda, const f
   return run_gemm(h, a_mn, b_mn, &p, 1, D, ldd, M, N, e, sumsq_tiles, 0, s);
 }
 
-int colsum(wgan_handle* h, const ColsumSeg* segs, int nseg, int N, float* out, cudaStream_t s) {
+// Up to three column-sum jobs in one launch pair: out_j[n] = sum_seg scale * sum_r X_seg[r, n].
+int colsum_jobs(wgan_handle* h, const ColsumJob* jobs, int njobs, cudaStream_t s) {
   ColsumArgs a;
   memset(&a, 0, sizeof a);
-  int maxrows = 1;
-  for (int i = 0; i < nseg; ++i) { a.seg[i] = segs[i]; if (segs[i].rows > maxrows) maxrows = segs[i].rows; }
-  a.nseg = nseg; a.N = N;
+  int maxrows = 1, maxN = 1;
+  for (int j = 0; j < njobs; ++j) {
+    a.job[j] = jobs[j];
+    if (jobs[j].N > maxN) maxN = jobs[j].N;
+    for (int i = 0; i < jobs[j].nseg; ++i)
+      if (jobs[j].seg[i].rows > maxrows) maxrows = jobs[j].seg[i].rows;
+  }
   int RC = cdiv(maxrows, 64);
   if (RC > 64) RC = 64;
   if (RC < 1) RC = 1;
-  dim3 grid(cdiv(N, 32), RC);
+  a.part_stride = h->colpart_stride;
+  dim3 grid(cdiv(maxN, 32), RC, njobs);
   colsum_partial_kernel<<<grid, 256, 0, s>>>(a, h->colpart);
   TRY(post_launch(h, "colsum_partial_kernel"));
-  colsum_final_kernel<<<cdiv(N, 256), 256, 0, s>>>(h->colpart, RC, N, out);
+  dim3 g2(cdiv(maxN, 256), njobs);
+  colsum_final_kernel<<<g2, 256, 0, s>>>(a, h->colpart, RC);
   return post_launch(h, "colsum_final_kernel");
+}
+
+int colsum(wgan_handle* h, const ColsumSeg* segs, int nseg, int N, float* out, cudaStream_t s) {
+  ColsumJob jb;
+  memset(&jb, 0, sizeof jb);
+  for (int i = 0; i < nseg; ++i) jb.seg[i] = segs[i];
+  jb.nseg = nseg; jb.N = N; jb.out = out;
+  return colsum_jobs(h, &jb, 1, s);
+}
+
+int segment_sums(wgan_handle* h, const SumJob* jobs, int njobs, cudaStream_t s) {
+  SumJobs a;
+  memset(&a, 0, sizeof a);
+  for (int j = 0; j < njobs; ++j) a.job[j] = jobs[j];
+  segment_sum_kernel<<<njobs, 1024, 0, s>>>(a);
+  return post_launch(h, "segment_sum_kernel");
 }
 
 // Bring a caller matrix into a TMA-legal layout (16 B aligned, ld % 4 == 0); copies only if needed.
@@ -490,12 +522,13 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   // ---- workspace ----
   const size_t R = h->R;
   h->nsq_tiles_max = cdiv(h->G, 32);
+  h->colpart_stride = 64 * (h->G > h->Hg ? (h->G > h->Hd ? h->G : h->Hd) : (h->Hg > h->Hd ? h->Hg : h->Hd));
   struct { float** p; size_t n; } allocs[] = {
       {&h->zbuf, R * h->Zl}, {&h->gh1, R * h->Hgl}, {&h->gh2, R * h->Hgl}, {&h->xcat, 3 * R * h->Gl},
       {&h->h1, 3 * R * h->Hdl}, {&h->h2, 3 * R * h->Hdl}, {&h->d2, 3 * R * h->Hdl}, {&h->d1, 3 * R * h->Hdl},
       {&h->dout, 3 * R}, {&h->v2, R * h->Hdl}, {&h->gd2, R * h->Hgl}, {&h->gd1, R * h->Hgl}, {&h->dz, R * h->Zl},
       {&h->nsq, static_cast<size_t>(h->nsq_tiles_max) * R}, {&h->crow, R}, {&h->pen, R}, {&h->norms, R},
-      {&h->colpart, static_cast<size_t>(64) * (h->G > h->Hg ? (h->G > h->Hd ? h->G : h->Hd) : (h->Hg > h->Hd ? h->Hg : h->Hd))},
+      {&h->colpart, static_cast<size_t>(3) * h->colpart_stride},
       {&h->sample_tmp, R * h->Gl}};
   for (auto& a : allocs) {
     if (cudaMalloc(a.p, (a.n + 64) * 4) != cudaSuccess) return fail("cudaMalloc(workspace) failed (max_batch too large?)");
@@ -631,10 +664,10 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
       gp ? -invB : 0.0f, a);
   TRY(post_launch(h, "critic_head_kernel"));
   float* sc = h->scalars(WGAN_NET_CRITIC);
-  segment_sum_kernel<<<1, 256, 0, s>>>(h->dout, Bl, 1, invB, 0.f, 0.f, sc + WGAN_S_DFAKE);
-  TRY(post_launch(h, "segment_sum_kernel"));
-  segment_sum_kernel<<<1, 256, 0, s>>>(h->dout + real0, Bl, 1, invB, 0.f, 0.f, sc + WGAN_S_DREAL);
-  TRY(post_launch(h, "segment_sum_kernel"));
+  {
+    SumJob jobs[2] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + real0, sc + WGAN_S_DREAL, Bl, invB}};
+    TRY(segment_sums(h, jobs, 2, s));
+  }
   // delta1 / g1 = (delta2 W2^T) . slope(h1)
   TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, T, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
 
@@ -652,8 +685,8 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
     gp_coef_kernel<<<ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s>>>(
         h->nsq, tiles, Bl, Bl, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, d1_hat, Hdl, Hd);
     TRY(post_launch(h, "gp_coef_kernel"));
-    segment_sum_kernel<<<1, 256, 0, s>>>(h->pen, Bl, 1, h->cfg.lambda_gp * invB, 0.f, 0.f, sc + WGAN_S_GP);
-    TRY(post_launch(h, "segment_sum_kernel"));
+    SumJob pj = {h->pen, sc + WGAN_S_GP, Bl, h->cfg.lambda_gp * invB};
+    TRY(segment_sums(h, &pj, 1, s));
     // parameter-gradient-of-norm pass: v1 = c . (gx W1) . s1 (in place over h1_hat), v2 = (v1 W2) . s2
     EpiParams ev1 = epi_mask(h1_hat, Hdl, a);
     ev1.row_scale = h->crow;
@@ -679,13 +712,19 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   }
   TRY(gemm1(h, true, true, h->h1, Hdl, h->d2, Hdl, h->Gr(T_W2), ldw2, Hd, Hd, T, epi_none(), s));
   {
-    ColsumSeg sb[3] = {{h->d1, Bl, Hdl, 1.0f}, {h->d1 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, 1.0f}, {}};
-    TRY(colsum(h, sb, 2, Hd, h->Gr(T_B1), s));
-    ColsumSeg s2[3] = {{h->d2, Bl, Hdl, 1.0f}, {h->d2 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, 1.0f}, {}};
-    TRY(colsum(h, s2, 2, Hd, h->Gr(T_B2), s));
-    ColsumSeg s3[3] = {{h->h2, Bl, Hdl, invB}, {h->h2 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, -invB},
-                       {h->v2, Bl, Hdl, 1.0f}};
-    TRY(colsum(h, s3, gp ? 3 : 2, Hd, h->Gr(T_W3), s));
+    ColsumJob jobs[3];
+    memset(jobs, 0, sizeof jobs);
+    jobs[0].seg[0] = ColsumSeg{h->d1, Bl, Hdl, 1.0f};
+    jobs[0].seg[1] = ColsumSeg{h->d1 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, 1.0f};
+    jobs[0].nseg = 2; jobs[0].N = Hd; jobs[0].out = h->Gr(T_B1);
+    jobs[1].seg[0] = ColsumSeg{h->d2, Bl, Hdl, 1.0f};
+    jobs[1].seg[1] = ColsumSeg{h->d2 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, 1.0f};
+    jobs[1].nseg = 2; jobs[1].N = Hd; jobs[1].out = h->Gr(T_B2);
+    jobs[2].seg[0] = ColsumSeg{h->h2, Bl, Hdl, invB};
+    jobs[2].seg[1] = ColsumSeg{h->h2 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, -invB};
+    jobs[2].seg[2] = ColsumSeg{h->v2, Bl, Hdl, 1.0f};
+    jobs[2].nseg = gp ? 3 : 2; jobs[2].N = Hd; jobs[2].out = h->Gr(T_W3);
+    TRY(colsum_jobs(h, jobs, 3, s));
     CK(cudaMemsetAsync(h->Gr(T_B3), 0, 4, s));           // sum(+1/B) + sum(-1/B) over equal row counts
   }
   return 0;
@@ -722,8 +761,8 @@ int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, 
       h->h2, Hdl, Bl, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, -invB, 0.f, 0.f, a);
   TRY(post_launch(h, "critic_head_kernel"));
   float* sc = h->scalars(WGAN_NET_GENERATOR);
-  segment_sum_kernel<<<1, 256, 0, s>>>(h->dout, Bl, 1, invB, 0.f, 0.f, sc + WGAN_S_DFAKE);
-  TRY(post_launch(h, "segment_sum_kernel"));
+  SumJob gj = {h->dout, sc + WGAN_S_DFAKE, Bl, invB};
+  TRY(segment_sums(h, &gj, 1, s));
   // back through the critic to the generated cells
   TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, Bl, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
   TRY(gemm1(h, false, false, h->d1, Hdl, W1, ldw1, d3, Gl, Bl, G, Hd, epi_mask(xt, Gl, a), s));
@@ -891,6 +930,7 @@ int wgan_get_buffer(wgan_handle* h, const char* name, float** dev_ptr, int* rows
   std::string n(name);
   if (n == "x_tilde") { *dev_ptr = h->xcat; *rows = h->R; *cols = h->G; *ld = h->Gl; }
   else if (n == "gx") { *dev_ptr = h->xcat + static_cast<size_t>(Bl) * h->Gl; *rows = Bl; *cols = h->G; *ld = h->Gl; }
+  else if (n == "xcat") { *dev_ptr = h->xcat; *rows = 3 * h->R; *cols = h->G; *ld = h->Gl; }
   else if (n == "norms") { *dev_ptr = h->norms; *rows = 1; *cols = Bl; *ld = Bl; }
   else if (n == "d") { *dev_ptr = h->dout; *rows = 1; *cols = 3 * h->R; *ld = 3 * h->R; }
   else if (n == "h1") { *dev_ptr = h->h1; *rows = 3 * h->R; *cols = h->Hd; *ld = h->Hdl; }

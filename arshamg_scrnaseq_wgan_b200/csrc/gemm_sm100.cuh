@@ -135,7 +135,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// tcgen05.ld of 32 consecutive fp32 columns of this thread's TMEM lane: issue, then (later) wait.
+// The wait lists v[] as in/out operands so the compiler cannot hoist any use of v above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -147,7 +149,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                 "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),
+                 "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]),
+                 "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+// 32 consecutive floats: eight 16 B loads when the whole chunk is in range and aligned,
+// guarded scalar loads (value `fill` out of range) otherwise.
+__device__ __forceinline__ void load_chunk32(const float* __restrict__ base, int n0, int N, bool vec_ok,
+                                             float fill, float (&out)[32]) {
+  if (vec_ok && n0 + 32 <= N) {
+    const float4* p4 = reinterpret_cast<const float4*>(base + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(p4 + j);
+      out[4 * j] = t.x; out[4 * j + 1] = t.y; out[4 * j + 2] = t.z; out[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = (n0 + j < N) ? __ldg(base + n0 + j) : fill;
+  }
 }
 
 // Shared-memory matrix descriptor (descriptor version 1 = Blackwell).
@@ -318,6 +345,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
       tcgen05_after_sync();
       float rs = 1.0f;
       if (fused && e.row_scale != nullptr && row_ok) rs = __ldg(e.row_scale + row);
+      const bool bias_vec = (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
+      const bool aux_vec = ((reinterpret_cast<uintptr_t>(e.aux) & 15) == 0) && ((e.ld_aux & 3) == 0);
       float sumsq = 0.0f;
       if (row0 < p.M) {
         const int nchunks = p.bn / 32;
@@ -325,24 +354,47 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           const int n0 = nt * p.bn + c * 32;
           if (n0 >= p.N) break;
           uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) +
-                        static_cast<uint32_t>(acc * p.bn + c * 32), v);
+          tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) +
+                              static_cast<uint32_t>(acc * p.bn + c * 32), v);
           if (fused) {
+            // epilogue operands are fetched while the TMEM load is in flight
+            float t[32];
+            if (e.bias != nullptr) {
+              load_chunk32(e.bias, n0, p.N, bias_vec, 0.0f, t);
+              tmem_ld32_wait(v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + j;
-              float y = __uint_as_float(v[j]);
-              if (e.bias != nullptr && n < p.N) y += __ldg(e.bias + n);
-              if (e.act == 1) y = fmaxf(y, e.alpha * y);
-              if (e.aux != nullptr) {
-                float h = 1.0f;
-                if (row_ok && n < p.N) h = __ldg(e.aux + static_cast<size_t>(row) * e.ld_aux + n);
-                y *= (h > 0.0f) ? 1.0f : e.alpha;
-              }
-              y *= rs;
-              if (n < p.N) sumsq += y * y;
-              v[j] = __float_as_uint(y);
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + t[j]);
+            } else {
+              tmem_ld32_wait(v);
             }
+            if (e.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float y = __uint_as_float(v[j]);
+                v[j] = __float_as_uint(fmaxf(y, e.alpha * y));
+              }
+            }
+            if (e.aux != nullptr) {
+              if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, t);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float sl = (row_ok && !(t[j] > 0.0f)) ? e.alpha : 1.0f;
+                v[j] = __float_as_uint(__uint_as_float(v[j]) * sl);
+              }
+            }
+            if (e.row_scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
+            }
+            if (e.row_sumsq != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float y = __uint_as_float(v[j]);
+                if (n0 + j < p.N) sumsq = fmaf(y, y, sumsq);
+              }
+            }
+          } else {
+            tmem_ld32_wait(v);
           }
           const uint32_t buf = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
           if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago is free again

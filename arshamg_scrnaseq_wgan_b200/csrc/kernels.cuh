@@ -46,14 +46,39 @@ __global__ void finish_splitk_kernel(const float* __restrict__ part, size_t slab
   }
 }
 
-// Sum `splits` slabs of a weight-gradient sized [rows, ld] (pads included) into the grad arena.
-__global__ void reduce_slabs_kernel(const float* __restrict__ part, size_t slab_stride, int splits,
-                                    float* __restrict__ out, size_t n) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+// Same as finish_splitk_kernel without row_sumsq: one thread per 4 consecutive columns, so that
+// small outputs with many splits (K = batch wgrads) still fill the machine.
+__global__ void finish_splitk_vec4_kernel(const float* __restrict__ part, size_t slab_stride, int splits,
+                                          float* out, int ld, int M, int N, EpiParams e) {
+  const int n4 = (N + 3) >> 2;
+  const size_t total = static_cast<size_t>(M) * n4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float y = 0.0f;
-    for (int s = 0; s < splits; ++s) y += part[s * slab_stride + i];
-    out[i] = y;
+    const int row = static_cast<int>(i / n4), n = static_cast<int>(i % n4) * 4;
+    const size_t off = static_cast<size_t>(row) * ld + n;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(part + s * slab_stride + off);
+      y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
+    }
+    float v[4] = {y.x, y.y, y.z, y.w};
+    const float rs = e.row_scale ? e.row_scale[row] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j >= N) { v[j] = 0.0f; continue; }
+      if (e.bias) v[j] += e.bias[n + j];
+      if (e.act == 1) v[j] = fmaxf(v[j], e.alpha * v[j]);
+      if (e.aux) {
+        const float h = e.aux[static_cast<size_t>(row) * e.ld_aux + n + j];
+        v[j] *= (h > 0.0f) ? 1.0f : e.alpha;
+      }
+      v[j] *= rs;
+    }
+    if (n + 4 <= N) {
+      *reinterpret_cast<float4*>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int j = 0; n + j < N; ++j) out[off + j] = v[j];
+    }
   }
 }
 
@@ -142,24 +167,30 @@ __global__ void critic_head_kernel(const float* __restrict__ h2, int ld, int row
   }
 }
 
-// Deterministic single-block segmented sum: out[i] = scale[i] * sum(d[i*seg .. (i+1)*seg)), i < nseg.
-__global__ void segment_sum_kernel(const float* __restrict__ d, int seg, int nseg, float s0, float s1,
-                                   float s2, float* __restrict__ out) {
+// Deterministic block sums: job j (= blockIdx.x) writes out_j[0] = scale_j * sum(ptr_j[0..n_j)).
+struct SumJob {
+  const float* ptr;
+  float* out;
+  int n;
+  float scale;
+};
+struct SumJobs {
+  SumJob job[3];
+};
+__global__ void __launch_bounds__(1024) segment_sum_kernel(SumJobs jobs) {
   __shared__ float red[32];
-  for (int g = 0; g < nseg; ++g) {
-    float acc = 0.0f;
-    for (int i = threadIdx.x; i < seg; i += blockDim.x) acc += d[static_cast<size_t>(g) * seg + i];
+  const SumJob jb = jobs.job[blockIdx.x];
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < jb.n; i += blockDim.x) acc += jb.ptr[i];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (threadIdx.x == 0) out[g] = v * (g == 0 ? s0 : (g == 1 ? s1 : s2));
-    }
-    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) jb.out[0] = v * jb.scale;
   }
 }
 
@@ -218,21 +249,27 @@ struct ColsumSeg {
   int ld;
   float scale;
 };
-struct ColsumArgs {
+struct ColsumJob {
   ColsumSeg seg[3];
+  float* out;
   int nseg;
   int N;
+};
+struct ColsumArgs {
+  ColsumJob job[3];       // blockIdx.z selects the job
+  int part_stride;        // floats of partial storage per job
 };
 
 __global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part) {
   __shared__ float red[8][33];
+  const ColsumJob& jb = a.job[blockIdx.z];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   const int RC = gridDim.y, rc = blockIdx.y;
   float acc = 0.0f;
-  if (n < a.N) {
-    for (int s = 0; s < a.nseg; ++s) {
-      const ColsumSeg sg = a.seg[s];
+  if (n < jb.N) {
+    for (int s = 0; s < jb.nseg; ++s) {
+      const ColsumSeg sg = jb.seg[s];
       const int per = (sg.rows + RC - 1) / RC;
       const int r0 = rc * per, r1 = min(r0 + per, sg.rows);
       float t = 0.0f;
@@ -242,21 +279,21 @@ __global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part) {
   }
   red[ty][tx] = acc;
   __syncthreads();
-  if (ty == 0 && n < a.N) {
+  if (ty == 0 && n < jb.N) {
     float t = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][tx];
-    part[static_cast<size_t>(rc) * a.N + n] = t;
+    part[static_cast<size_t>(blockIdx.z) * a.part_stride + static_cast<size_t>(rc) * jb.N + n] = t;
   }
 }
 
-__global__ void colsum_final_kernel(const float* __restrict__ part, int RC, int N,
-                                    float* __restrict__ out) {
+__global__ void colsum_final_kernel(ColsumArgs a, const float* __restrict__ part, int RC) {
+  const ColsumJob& jb = a.job[blockIdx.y];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  if (n >= jb.N) return;
   float t = 0.0f;
-  for (int r = 0; r < RC; ++r) t += part[static_cast<size_t>(r) * N + n];
-  out[n] = t;
+  for (int r = 0; r < RC; ++r) t += part[static_cast<size_t>(blockIdx.y) * a.part_stride + static_cast<size_t>(r) * jb.N + n];
+  jb.out[n] = t;
 }
 
 // ---------------------------------------------------------------------------------------------

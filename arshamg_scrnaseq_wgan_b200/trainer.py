@@ -322,16 +322,23 @@ class WGANTrainer:
         buf = torch.zeros((n, self.Gl), device=f"cuda:{self.device}", dtype=torch.float32)
         buf[:, :g] = cells_by_genes.to(buf.device, torch.float32)
         self._data = buf
-        self._xbuf = torch.zeros((self.max_batch, self.Gl), device=buf.device, dtype=torch.float32)
+
+    def real_slot(self, rows: int) -> torch.Tensor:
+        """The rows of the library's stacked activation buffer [fake | interpolate | real] where the
+        critic step expects the real cells; gathering straight into it lets layer 1 and its weight
+        gradient run as single GEMMs over the stacked rows (no staging copy)."""
+        xcat = self.buffer("xcat")
+        r0 = (2 if self.cfg.lambda_gp != 0 else 1) * rows
+        return xcat[r0:r0 + rows]
 
     def gather(self, idx: torch.Tensor) -> torch.Tensor:
         rows = idx.numel()
-        out = self._xbuf[:rows]
+        out = self.real_slot(rows)
         rc = self.lib.wgan_gather_rows(C.c_void_p(self._data.data_ptr()), self.Gl, C.c_void_p(idx.data_ptr()),
                                        C.c_void_p(out.data_ptr()), self.Gl, rows, self.cfg.gex_size, _stream())
         if rc != 0:
             raise _lib.WganError("gather_rows: " + self.lib.wgan_last_error(None).decode())
-        return out[:, :self.cfg.gex_size]
+        return out
 
     def train_iteration_resident(self, it: int, batch: int, seed: int = 0, read: bool = False):
         """One WGAN-GP iteration with everything drawn on the device: n_critic critic updates
