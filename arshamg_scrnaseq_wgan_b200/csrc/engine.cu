@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <string>
@@ -73,6 +74,7 @@ struct wgan_handle {
   size_t splitws_n;
   int nsq_tiles_max;
   int last_gx_rows;
+  int gemm_cluster;                  // preferred cluster size of the tensor-core GEMM (1, 2 or 4)
 
   float* P(int t) { return arena[td[t].net][WGAN_KIND_PARAM] + td[t].offset; }
   float* Gr(int t) { return arena[td[t].net][WGAN_KIND_GRAD] + td[t].offset; }
@@ -143,7 +145,9 @@ int make_map_2d(wgan_handle* h, CUtensorMap* m, const float* ptr, uint64_t inner
   cuuint32_t estr[2] = {1, 1};
   // operands are read as TF32 (round-to-nearest on load); MN-major 32-bit operands must use the
   // 32-byte-atom flavour of the 128 B swizzle (see make_smem_desc in gemm_sm100.cuh)
-  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
+  static const bool plain_f32 = getenv("WGAN_B200_TMA_F32") != nullptr;   // experiment: no TF32 rounding in TMA
+  CUresult r = h->encode(m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                         const_cast<float*>(ptr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -167,11 +171,15 @@ int make_map_out(wgan_handle* h, CUtensorMap* m, float* ptr, uint64_t N, uint64_
   return 0;
 }
 
+// N tile: minimise the tensor-pipe time of one M tile, n_tiles * (43 + bn/2) cycles per UMMA_K step
+// (measured on B200: a cta_group::1 M=128 tcgen05.mma costs ~43 + N/2 cycles, scripts/ubench/mma_rate.cu);
+// ties go to the wider tile (fewer re-reads of A).
 int pick_bn(int N) {
-  int best = 256, best_pad = 1 << 30;
+  int best = 256;
+  long best_cost = 1L << 60;
   for (int bn = 256; bn >= 32; bn -= 32) {
-    int pad = cdiv(N, bn) * bn;
-    if (pad < best_pad) { best_pad = pad; best = bn; }
+    const long cost = static_cast<long>(cdiv(N, bn)) * (86 + bn);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
@@ -200,16 +208,41 @@ int launch_finish(wgan_handle* h, const float* part, size_t slab, int splits, fl
   return post_launch(h, "finish_splitk_kernel");
 }
 
+// Launches min(cluster_tiles, co-resident clusters) clusters of p.cluster persistent CTAs.
 template <bool A_MN, bool B_MN>
-int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int grid, cudaStream_t s) {
+int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int cluster_tiles, cudaStream_t s) {
   static bool attr_set[16] = {};
+  static int max_clusters[16][5] = {};
   int dev = h->cfg.device & 15;
   if (!attr_set[dev]) {
     CK(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             232448));
     attr_set[dev] = true;
   }
-  gemm_tf32_kernel<A_MN, B_MN><<<grid, GEMM_THREADS, smem, s>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters[dev][p.cluster] == 0) {
+    int n = 0;
+    cfg.gridDim = dim3(h->num_sms / p.cluster * p.cluster);
+    if (p.cluster == 1 || cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<A_MN, B_MN>, &cfg) != cudaSuccess ||
+        n <= 0)
+      n = h->num_sms / p.cluster;
+    (void)cudaGetLastError();
+    max_clusters[dev][p.cluster] = n;
+  }
+  int clusters = cluster_tiles < max_clusters[dev][p.cluster] ? cluster_tiles : max_clusters[dev][p.cluster];
+  cfg.gridDim = dim3(clusters * p.cluster);
+  CK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN>, p));
   return post_launch(h, "gemm_tf32_kernel");
 }
 
@@ -244,6 +277,10 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   const int bn = pick_bn(N);
   const int m_tiles = cdiv(M, BM), n_tiles = cdiv(N, bn);
   const int tiles = m_tiles * n_tiles;
+  // CTAs of a cluster take adjacent M tiles and share the B tile through TMA multicast
+  int cluster = h->gemm_cluster;
+  while (cluster > 1 && (m_tiles < cluster || (bn / 32) % cluster != 0)) cluster >>= 1;
+  const int m_groups = cdiv(m_tiles, cluster);
   int stages;
   const size_t smem = gemm_smem_bytes(bn, &stages);
 
@@ -282,7 +319,7 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     memset(&p, 0, sizeof p);
     if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, BM, false));
     else       TRY(make_map_2d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, 32, 32, true));
-    if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, bn, false));
+    if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, bn / cluster, false));
     else       TRY(make_map_2d(h, &p.tma_b, pt.B, N, pt.K, pt.ldb, 32, 32, true));
     TRY(make_map_out(h, &p.tma_d, out + (direct ? 0 : slab * slab0), N, M, splits[i], ldd, slab));
     p.M = M; p.N = N; p.K = pt.K;
@@ -292,12 +329,17 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     p.m_tiles = m_tiles; p.n_tiles = n_tiles;
     p.stages = stages;
     p.total_kb = cdiv(pt.K, BK);
+    p.cluster = cluster;
+    p.m_groups = m_groups;
+    // operands that stream from HBM are prefetched into L2 a few K blocks ahead of the smem ring
+    static const bool l2_prefetch = getenv("WGAN_B200_L2_PREFETCH") != nullptr;   // measured: no gain, off
+    p.prefetch_a = (l2_prefetch && static_cast<size_t>(M) * pt.K * 4 > (8u << 20)) ? 1 : 0;
+    p.prefetch_b = (l2_prefetch && static_cast<size_t>(N) * pt.K * 4 > (8u << 20)) ? 1 : 0;
     // partials that go to the workspace stay raw (p.epi is all-zero) even when this part has a
     // single split; finish_splitk_kernel applies the epilogue after summing the slabs
     if (direct) p.epi = epi;
     else p.splits = splits[i];
-    int grid = tiles * splits[i];
-    if (grid > h->num_sms) grid = h->num_sms;
+    const int grid = m_groups * n_tiles * splits[i];       // cluster tiles; launch_tc caps at residency
     if (!a_mn && b_mn) TRY((launch_tc<false, true>(h, p, smem, grid, s)));
     else if (!a_mn && !b_mn) TRY((launch_tc<false, false>(h, p, smem, grid, s)));
     else if (a_mn && b_mn) TRY((launch_tc<true, true>(h, p, smem, grid, s)));
@@ -453,6 +495,11 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->cfg = *cfg;
   h->launches = 0;
   h->last_gx_rows = 0;
+  h->gemm_cluster = 1;
+  if (const char* env = getenv("WGAN_B200_GEMM_CLUSTER")) {
+    int c = atoi(env);
+    if (c == 1 || c == 2 || c == 4) h->gemm_cluster = c;
+  }
   for (int n = 0; n < 2; ++n) { for (int k = 0; k < 4; ++k) h->arena[n][k] = nullptr; h->powers[n] = nullptr; }
   h->zbuf = h->gh1 = h->gh2 = h->xcat = h->h1 = h->h2 = h->d2 = h->d1 = h->dout = h->v2 = h->gd2 = h->gd1 =
       h->dz = h->nsq = h->crow = h->pen = h->norms = h->colpart = h->splitws = h->sample_tmp = nullptr;

@@ -30,6 +30,7 @@ constexpr int GEMM_THREADS = 192;
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_BOX_BYTES = 32 * 32 * 4;   // one [32 rows][32 cols] fp32 staging box
 constexpr int EPI_BUFS = 8;                   // 4 epilogue warps x 2
+constexpr int PREFETCH_DIST = 12;             // K blocks between the L2 prefetch and the smem load
 
 struct EpiParams {
   const float* bias;        // [N] or nullptr
@@ -53,6 +54,10 @@ struct GemmParams {
   int m_tiles, n_tiles;
   int stages;
   int total_kb;
+  int cluster;              // CTAs per cluster (1, 2 or 4) along M: they share the B tile by TMA multicast
+  int m_groups;             // ceil(m_tiles / cluster)
+  int prefetch_a;           // 1: TMA-prefetch A tiles into L2 PREFETCH_DIST K blocks ahead
+  int prefetch_b;
   EpiParams epi;
 };
 
@@ -101,6 +106,48 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Warp-uniform leader election: the issuing warps keep their control flow (and therefore the TMA /
+// UMMA descriptor arithmetic) uniform and predicate only the issue itself on the elected lane, so
+// the operands live in uniform registers instead of being funnelled through R2UR per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1,
                                              int c2) {
   asm volatile(
@@ -124,6 +171,12 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -227,7 +280,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(full_bar + 8 * s, 1);
-        mbar_init(empty_bar + 8 * s, 1);
+        mbar_init(empty_bar + 8 * s, static_cast<uint32_t>(p.cluster));   // one commit per cluster CTA
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar + 8 * a, 1);
@@ -244,31 +297,59 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   }
   tcgen05_before_sync();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();       // peers' barriers are initialised before any multicast
   tcgen05_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  // Persistent schedule over "cluster tiles": the C CTAs of a cluster take C consecutive M tiles of
+  // the same N tile and split, and walk the K blocks in lockstep.
+  const int C = p.cluster;
+  const uint32_t crank = (C > 1) ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1u);
+  const int total_tiles = p.m_groups * p.n_tiles * p.splits;
+  const int tile0 = blockIdx.x / C, tile_step = gridDim.x / C;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mt = (tile / p.n_tiles) % p.m_tiles;
-        const int z = tile / (p.n_tiles * p.m_tiles);
-        const int m0 = mt * BM, n0 = nt * p.bn;
-        const int kb0 = z * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
-          const uint32_t fb = full_bar + 8 * stage;
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const int nt = tile % p.n_tiles;
+      const int mt = ((tile / p.n_tiles) % p.m_groups) * C + static_cast<int>(crank);
+      const int z = tile / (p.n_tiles * p.m_groups);
+      const int m0 = mt * BM, n0 = nt * p.bn;
+      const int kb0 = z * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
+        const uint32_t fb = full_bar + 8 * stage;
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint32_t sb = sa + a_bytes;
+        const int k0 = kb * BK;
+        if (elect_one()) {
+          // HBM latency (~2 us under load) exceeds what the smem ring can cover for a streaming
+          // operand: pull the tile PREFETCH_DIST K blocks ahead into L2 first
+          const int kp = kb + PREFETCH_DIST;
+          if (kp < kb1) {
+            const int kp0 = kp * BK;
+            if (p.prefetch_a) {
+              if (!A_MN) {
+                tma_prefetch_2d(&p.tma_a, kp0, m0);
+              } else {
+#pragma unroll
+                for (int c = 0; c < BM / 32; ++c) tma_prefetch_2d(&p.tma_a, m0 + 32 * c, kp0);
+              }
+            }
+            if (p.prefetch_b && crank == 0) {
+              if (!B_MN) {
+                for (int r = 0; r < C; ++r) tma_prefetch_2d(&p.tma_b, kp0, n0 + r * (p.bn / C));
+              } else {
+                for (int c = 0; c < p.bn / 32; ++c) tma_prefetch_2d(&p.tma_b, n0 + 32 * c, kp0);
+              }
+            }
+          }
           mbar_expect_tx(fb, stage_bytes);
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + a_bytes;
-          const int k0 = kb * BK;
           if (!A_MN) {
             tma_load_2d(sa, &p.tma_a, fb, k0, m0);                       // box [128 rows][32 k]
           } else {
@@ -276,55 +357,74 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
             for (int c = 0; c < BM / 32; ++c)                            // boxes [32 k][32 m]
               tma_load_2d(sa + c * 4096, &p.tma_a, fb, m0 + 32 * c, k0);
           }
-          if (!B_MN) {
-            tma_load_2d(sb, &p.tma_b, fb, k0, n0);                       // box [bn rows][32 k]
+          if (C == 1) {
+            if (!B_MN) {
+              tma_load_2d(sb, &p.tma_b, fb, k0, n0);                     // box [bn rows][32 k]
+            } else {
+              for (int c = 0; c < p.bn / 32; ++c)                        // boxes [32 k][32 n]
+                tma_load_2d(sb + c * 4096, &p.tma_b, fb, n0 + 32 * c, k0);
+            }
           } else {
-            for (int c = 0; c < p.bn / 32; ++c)                          // boxes [32 k][32 n]
-              tma_load_2d(sb + c * 4096, &p.tma_b, fb, n0 + 32 * c, k0);
+            // every CTA fetches 1/C of the shared B tile and multicasts it to the whole cluster
+            if (!B_MN) {
+              const int rows_per = p.bn / C;                             // tma_b box = [bn/C rows][32 k]
+              tma_load_2d_mc(sb + crank * rows_per * 128, &p.tma_b, fb, k0, n0 + crank * rows_per, cmask);
+            } else {
+              for (int c = crank; c < p.bn / 32; c += C)
+                tma_load_2d_mc(sb + c * 4096, &p.tma_b, fb, n0 + 32 * c, k0, cmask);
+            }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                             ((B_MN ? 1u : 0u) << 16) | (static_cast<uint32_t>(p.bn >> 3) << 17) |
-                             (static_cast<uint32_t>(BM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int z = tile / (p.n_tiles * p.m_tiles);
-        const int kb0 = z * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                           ((B_MN ? 1u : 0u) << 16) | (static_cast<uint32_t>(p.bn >> 3) << 17) |
+                           (static_cast<uint32_t>(BM >> 4) << 24);
+    // smem descriptors: only the 14-bit start-address field changes per stage / K step
+    const uint64_t a_proto = A_MN ? make_smem_desc(0, 4096, 512, 1) : make_smem_desc(0, 16, 1024, 2);
+    const uint64_t b_proto = B_MN ? make_smem_desc(0, 4096, 512, 1) : make_smem_desc(0, 16, 1024, 2);
+    const uint32_t a_hi = static_cast<uint32_t>(a_proto >> 32), b_hi = static_cast<uint32_t>(b_proto >> 32);
+    const uint32_t a_lo0 = static_cast<uint32_t>(a_proto) | ((smem_base >> 4) & 0x3FFFu);
+    const uint32_t b_lo0 = static_cast<uint32_t>(b_proto) | (((smem_base + a_bytes) >> 4) & 0x3FFFu);
+    constexpr uint32_t a_kstep = A_MN ? (1024u >> 4) : (32u >> 4);
+    constexpr uint32_t b_kstep = B_MN ? (1024u >> 4) : (32u >> 4);
+    const uint32_t stage_step = stage_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      const int z = tile / (p.n_tiles * p.m_groups);
+      const int kb0 = z * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
+      tcgen05_after_sync();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.bn);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + 8 * stage, phase);
         tcgen05_after_sync();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.bn);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
-          tcgen05_after_sync();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + a_bytes;
+        const uint32_t a_lo = a_lo0 + stage * stage_step;
+        const uint32_t b_lo = b_lo0 + stage * stage_step;
+        if (elect_one()) {
 #pragma unroll
-          for (int s = 0; s < BK / UMMA_K; ++s) {
-            const uint64_t adesc = A_MN ? make_smem_desc(sa + s * 1024, 4096, 512, 1)
-                                        : make_smem_desc(sa + s * 32, 16, 1024, 2);
-            const uint64_t bdesc = B_MN ? make_smem_desc(sb + s * 1024, 4096, 512, 1)
-                                        : make_smem_desc(sb + s * 32, 16, 1024, 2);
-            umma_tf32(d_tmem, adesc, bdesc, idesc, (kb > kb0 || s > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar + 8 * stage);      // frees the smem slot when these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          for (int s = 0; s < BK / UMMA_K; ++s)
+            umma_tf32(d_tmem, pack64(a_lo + s * a_kstep, a_hi), pack64(b_lo + s * b_kstep, b_hi), idesc,
+                      (kb > kb0 || s > 0) ? 1u : 0u);
+          // frees the smem slot (in every CTA of the cluster: peers multicast into it) when these MMAs retire
+          if (C == 1) umma_commit(empty_bar + 8 * stage);
+          else umma_commit_mc(empty_bar + 8 * stage, cmask);
+          if (kb == kb1 - 1) umma_commit(tfull_bar + 8 * acc);   // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar + 8 * acc);          // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue warps (TMEM -> regs -> smem -> TMA store) =====================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
@@ -332,10 +432,10 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
     const bool fused = (p.splits == 1);
     uint32_t nstore = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int nt = tile % p.n_tiles;
-      const int mt = (tile / p.n_tiles) % p.m_tiles;
-      const int z = tile / (p.n_tiles * p.m_tiles);
+      const int mt = ((tile / p.n_tiles) % p.m_groups) * C + static_cast<int>(crank);
+      const int z = tile / (p.n_tiles * p.m_groups);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = mt * BM + 32 * q;
@@ -428,6 +528,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
 
   tcgen05_before_sync();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();       // no peer commit / multicast may target an exited CTA
   tcgen05_after_sync();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
