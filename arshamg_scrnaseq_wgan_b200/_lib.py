@@ -53,6 +53,7 @@ SIGNATURES = {
     "wgan_generator_grads": (_I, [_P, _P, _I, _I, _I, _P]),
     "wgan_generator_apply": (_I, [_P, _P]),
     "wgan_sample": (_I, [_P, _P, _I, _P, _I, _I, _P]),
+    "wgan_critic_forward": (_I, [_P, _P, _I, _P, _I, _P]),
     "wgan_latent_fit_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _F, _P]),
     "wgan_rng_noise_prior": (_I, [_P, _I, C.c_int64, _I, _I, _F, C.c_uint64, C.c_uint32, _P]),
     "wgan_rng_uniform": (_I, [_P, C.c_int64, _I, C.c_uint64, C.c_uint32, _P]),

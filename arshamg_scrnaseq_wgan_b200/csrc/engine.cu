@@ -857,6 +857,29 @@ int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Critic forward only: d = D(x)   [W:103-124]
+// ---------------------------------------------------------------------------------------------
+int wgan_critic_forward(wgan_handle* h, const float* x_dev, int ldx, float* d_out_dev, int rows,
+                        wgan_stream_t stream) {
+  if (!h) return -2;
+  if (!x_dev || !d_out_dev) FAIL("critic_forward: null argument");
+  TRY(check_rows(h, rows, rows));
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Hd = h->Hd, Hdl = h->Hdl;
+  const float a = h->cfg.alpha;
+  const float* x; int lx;
+  TRY(stage_input(h, x_dev, ldx, rows, h->G, h->xcat, h->Gl, &x, &lx, s));
+  TRY(gemm1(h, false, true, x, lx, h->P(T_W1), h->td[T_W1].ld, h->h1, Hdl, rows, Hd, h->G,
+            epi_bias_lrelu(h->P(T_B1), a), s));
+  TRY(gemm1(h, false, true, h->h1, Hdl, h->P(T_W2), h->td[T_W2].ld, h->h2, Hdl, rows, Hd, Hd,
+            epi_bias_lrelu(h->P(T_B2), a), s));
+  critic_head_kernel<<<ew_grid(static_cast<size_t>(rows) * 32, 256, h->num_sms), 256, 0, s>>>(
+      h->h2, Hdl, rows, Hd, h->P(T_W3), h->P(T_B3), d_out_dev, h->d2, rows, 0.f, 0.f, 0.f, a);
+  return post_launch(h, "critic_head_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Latent-vector fit step (build-defined workload)
 // ---------------------------------------------------------------------------------------------
 int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_dev, float* powers_dev,

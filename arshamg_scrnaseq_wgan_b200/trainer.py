@@ -281,6 +281,14 @@ class WGANTrainer:
         self._ck(self.lib.wgan_sample(self._h, zp, ldz, op, ldo, rows, _stream()), "sample")
         return out
 
+    def discriminator(self, x) -> torch.Tensor:
+        """D(x) [W:103-124]: [rows, gex] -> [rows, 1] (linear output, no sigmoid)."""
+        xp, ldx, rows = self._mat(x, self.cfg.gex_size)
+        out = torch.empty((rows, 1), device=x.device, dtype=torch.float32)
+        self._ck(self.lib.wgan_critic_forward(self._h, xp, ldx, C.c_void_p(out.data_ptr()), rows, _stream()),
+                 "critic_forward")
+        return out
+
     def noise_prior(self, batch_size: int, dim: Optional[int] = None, seed: int = 0, call_id: Optional[int] = None,
                     row0: Optional[int] = None, data_max_value: float = 1.0) -> torch.Tensor:
         """abs(Normal(0, data_max/10) + Poisson(1)) [W:91-94], drawn on the device (Philox)."""
@@ -434,3 +442,8 @@ class WGANTrainer:
 def generator(trainer: WGANTrainer, z, reuse: bool = False):
     """Functional alias with the reference signature generator(z, reuse) [W:61]."""
     return trainer.generator(z)
+
+
+def discriminator(trainer: WGANTrainer, x, reuse: bool = False):
+    """Functional alias with the reference signature discriminator(x, reuse) [W:103]."""
+    return trainer.discriminator(x)

@@ -101,6 +101,10 @@ int wgan_generator_apply(wgan_handle* h, wgan_stream_t stream);
 int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int ld_out, int rows,
                 wgan_stream_t stream);
 
+/* ---- critic forward only: d_out[rows] = D(x) (replaces fetching D_real / D_fake [W:129-130]) ---- */
+int wgan_critic_forward(wgan_handle* h, const float* x_dev, int ldx, float* d_out_dev, int rows,
+                        wgan_stream_t stream);
+
 /* ---- latent-vector fit (build-defined): one Adam step on z minimising
  *      sum_g (G(z) - x)^2 per cell with G frozen.  z_dev [rows, noise] (ld = noise) is
  *      updated in place; m_dev/v_dev same shape; powers_dev = {beta1_power, beta2_power};
