@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -75,6 +76,7 @@ struct wgan_handle {
   int nsq_tiles_max;
   int last_gx_rows;
   int gemm_cluster;                  // preferred cluster size of the tensor-core GEMM (1, 2 or 4)
+  int gemm_msub;                     // 0 = auto, 1 / 2 = force 128- / 256-row CTA tiles
 
   float* P(int t) { return arena[td[t].net][WGAN_KIND_PARAM] + td[t].offset; }
   float* Gr(int t) { return arena[td[t].net][WGAN_KIND_GRAD] + td[t].offset; }
@@ -184,12 +186,14 @@ int pick_bn(int N) {
   return best;
 }
 
-size_t gemm_smem_bytes(int bn, int* stages_out) {
+size_t gemm_smem_bytes(int bn, int msub, int* stages_out) {
   const size_t budget = 232448;                       // 227 KB opt-in maximum per CTA
   const size_t fixed = 1024 + EPI_BUFS * EPI_BOX_BYTES + 256;
-  const size_t stage = BM * 128 + static_cast<size_t>(bn) * 128;
+  const size_t stage = static_cast<size_t>(BM) * msub * 128 + static_cast<size_t>(bn) * 128;
   int stages = static_cast<int>((budget - fixed) / stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  static const int cap = getenv("WGAN_B200_GEMM_STAGES") ? atoi(getenv("WGAN_B200_GEMM_STAGES")) : 0;   // experiments
+  if (cap > 0 && stages > cap) stages = cap;
   *stages_out = stages;
   size_t need = fixed + stages * stage;
   if (need < 120 * 1024) need = 120 * 1024;           // force 1 CTA/SM: each CTA allocates all of TMEM
@@ -248,8 +252,10 @@ int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int cluster_tile
 
 // D[M,N] = epi( sum_parts A_i * B_i ).  a_mn/b_mn: operand majors (see gemm_sm100.cuh).
 int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts, float* D, int ldd,
-             int M, int N, const EpiParams& epi, int* sumsq_tiles, int force_splits, cudaStream_t s) {
+             int M, int N, const EpiParams& epi, int* sumsq_tiles, int force_splits, cudaStream_t s,
+             float* blend_out = nullptr) {
   if (M <= 0 || N <= 0) FAIL("gemm: empty output %dx%d", M, N);
+  if (epi.blend_x != nullptr) force_splits = 1;       // the second output only exists in the fused epilogue
   for (int i = 0; i < nparts; ++i)
     if (parts[i].K <= 0) FAIL("gemm: empty K");
   const size_t slab = round64(static_cast<size_t>(M) * ldd);
@@ -270,19 +276,37 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
       TRY(post_launch(h, "gemm_fp32_kernel"));
     }
     TRY(launch_finish(h, raw, slab, nparts, D, ldd, M, N, epi, s));
+    if (epi.blend_x != nullptr) {
+      blend_kernel<<<ew_grid(static_cast<size_t>(M) * (ldd / 4), 256, h->num_sms), 256, 0, s>>>(
+          epi.blend_x, epi.ld_blend, D, ldd, epi.blend_eps, blend_out, ldd, M, ldd / 4);
+      TRY(post_launch(h, "blend_kernel"));
+    }
     if (sumsq_tiles) *sumsq_tiles = 1;
     return 0;
   }
 
-  const int bn = pick_bn(N);
-  const int m_tiles = cdiv(M, BM), n_tiles = cdiv(N, bn);
+  static const int bn_cap = getenv("WGAN_B200_GEMM_BN") ? atoi(getenv("WGAN_B200_GEMM_BN")) : 0;          // experiments
+  const int bn = (bn_cap >= 32 && bn_cap % 32 == 0 && pick_bn(N) > bn_cap) ? bn_cap : pick_bn(N);
+  const int n_tiles = cdiv(N, bn);
+  // 256-row CTA tiles (two 128-row accumulators sharing the B tile in smem) halve the B bytes per
+  // FLOP; used whenever the output still has enough tiles (x possible K splits) to fill the machine
+  int msub = 1;
+  {
+    int min_kb = 1 << 30;
+    for (int i = 0; i < nparts; ++i) min_kb = std::min(min_kb, cdiv(parts[i].K, BK));
+    const long units2 = static_cast<long>(cdiv(M, 2 * BM)) * n_tiles * nparts * std::max(1, min_kb / 8);
+    (void)units2;   // measured (profiles/r01_gemm_shape_sweeps.txt): 256-row tiles lose more to the shallower ring
+    if (h->gemm_msub == 2 && M >= 2 * BM) msub = 2;   // than they gain from B reuse on every WGAN shape: opt-in only
+  }
+  const int nacc = (2 * msub * bn <= 512) ? 2 : 1;
+  const int m_tiles = cdiv(M, BM * msub);
   const int tiles = m_tiles * n_tiles;
   // CTAs of a cluster take adjacent M tiles and share the B tile through TMA multicast
   int cluster = h->gemm_cluster;
   while (cluster > 1 && (m_tiles < cluster || (bn / 32) % cluster != 0)) cluster >>= 1;
   const int m_groups = cdiv(m_tiles, cluster);
   int stages;
-  const size_t smem = gemm_smem_bytes(bn, &stages);
+  const size_t smem = gemm_smem_bytes(bn, msub, &stages);
 
   // split-K policy: fill ~2 waves when the output has few tiles, at least 8 k-blocks per split
   int splits[2], kbps[2], total_splits = 0;
@@ -291,7 +315,7 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     int sp = 1;
     if (force_splits > 0) {
       sp = force_splits;
-    } else if (tiles * nparts < h->num_sms) {
+    } else if (tiles * nparts * 2 <= h->num_sms) {       // at most half the SMs would have a tile
       sp = cdiv(2 * h->num_sms, tiles * nparts);
       if (sp > total_kb / 8) sp = total_kb / 8;
     }
@@ -317,11 +341,13 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     const Part& pt = parts[i];
     GemmParams p;
     memset(&p, 0, sizeof p);
-    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, BM, false));
+    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, BM * msub, false));
     else       TRY(make_map_2d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, 32, 32, true));
     if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, bn / cluster, false));
     else       TRY(make_map_2d(h, &p.tma_b, pt.B, N, pt.K, pt.ldb, 32, 32, true));
     TRY(make_map_out(h, &p.tma_d, out + (direct ? 0 : slab * slab0), N, M, splits[i], ldd, slab));
+    if (direct && epi.blend_x != nullptr)
+      TRY(make_map_out(h, &p.tma_d2, blend_out, N, M, 1, ldd, slab));
     p.M = M; p.N = N; p.K = pt.K;
     p.bn = bn;
     p.splits = direct ? 1 : splits[i];
@@ -331,6 +357,8 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     p.total_kb = cdiv(pt.K, BK);
     p.cluster = cluster;
     p.m_groups = m_groups;
+    p.msub = msub;
+    p.nacc = nacc;
     // operands that stream from HBM are prefetched into L2 a few K blocks ahead of the smem ring
     static const bool l2_prefetch = getenv("WGAN_B200_L2_PREFETCH") != nullptr;   // measured: no gain, off
     p.prefetch_a = (l2_prefetch && static_cast<size_t>(M) * pt.K * 4 > (8u << 20)) ? 1 : 0;
@@ -432,15 +460,17 @@ int stage_input(wgan_handle* h, const float* src, int ld, int rows, int cols, fl
 
 // Generator forward [W:61-83]: gh1, gh2 and x~ (into `xt`, ld `ldxt`).
 int generator_forward(wgan_handle* h, const float* z, int ldz, int rows, float* xt, int ldxt,
-                      cudaStream_t s) {
+                      cudaStream_t s, const float* blend_x = nullptr, int ld_blend = 0,
+                      const float* blend_eps = nullptr, float* blend_out = nullptr) {
   const float a = h->cfg.alpha;
   TRY(gemm1(h, false, true, z, ldz, h->P(T_WG1), h->td[T_WG1].ld, h->gh1, h->Hgl, rows, h->Hg, h->Z,
             epi_bias_lrelu(h->P(T_BG1), a), s));
   TRY(gemm1(h, false, true, h->gh1, h->Hgl, h->P(T_WG2), h->td[T_WG2].ld, h->gh2, h->Hgl, rows, h->Hg,
             h->Hg, epi_bias_lrelu(h->P(T_BG2), a), s));
-  TRY(gemm1(h, false, true, h->gh2, h->Hgl, h->P(T_WG3), h->td[T_WG3].ld, xt, ldxt, rows, h->G, h->Hg,
-            epi_bias_lrelu(h->P(T_BG3), a), s));
-  return 0;
+  EpiParams e3 = epi_bias_lrelu(h->P(T_BG3), a);
+  e3.blend_x = blend_x; e3.ld_blend = ld_blend; e3.blend_eps = blend_eps;
+  Part p3{h->gh2, h->Hgl, h->P(T_WG3), h->td[T_WG3].ld, h->Hg};
+  return run_gemm(h, false, true, &p3, 1, xt, ldxt, rows, h->G, e3, nullptr, 0, s, blend_out);
 }
 
 int check_rows(wgan_handle* h, int rows, int global_batch) {
@@ -496,6 +526,11 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->launches = 0;
   h->last_gx_rows = 0;
   h->gemm_cluster = 1;
+  h->gemm_msub = 0;
+  if (const char* env = getenv("WGAN_B200_GEMM_MSUB")) {
+    int c = atoi(env);
+    if (c == 1 || c == 2) h->gemm_msub = c;
+  }
   if (const char* env = getenv("WGAN_B200_GEMM_CLUSTER")) {
     int c = atoi(env);
     if (c == 1 || c == 2 || c == 4) h->gemm_cluster = c;
@@ -685,13 +720,10 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
 
   // generator forward (constant in this step)
   float* xt = h->xcat;
-  TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
   float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;    // interpolates, later overwritten by gx
-  if (gp) {
-    blend_kernel<<<ew_grid(static_cast<size_t>(Bl) * (Gl / 4), 256, h->num_sms), 256, 0, s>>>(
-        x, lx, xt, Gl, eps_dev, xh, Gl, Bl, Gl / 4);
-    TRY(post_launch(h, "blend_kernel"));
-  }
+  // the interpolate x^ = eps x + (1 - eps) x~ is a second output of the generator-output GEMM
+  if (gp) TRY(generator_forward(h, z, lz, Bl, xt, Gl, s, x, lx, eps_dev, xh));
+  else TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
 
   // critic layer 1 on [fake | hat | real]  [W:107-111]
   const EpiParams e1 = epi_bias_lrelu(h->P(T_B1), a);

@@ -40,13 +40,18 @@ struct EpiParams {
   int ld_aux;
   int act;                  // 0 = identity, 1 = LeakyReLU(alpha)
   float alpha;
-  int pad_;
+  int ld_blend;
+  // second output (tma_d2): y2 = eps[m] * blend_x[m,n] + (1 - eps[m]) * y  -- the WGAN-GP interpolate
+  // x_hat written by the generator-output GEMM itself; nullptr = off
+  const float* blend_x;
+  const float* blend_eps;
 };
 
 struct GemmParams {
   CUtensorMap tma_a;        // 64 B aligned by the driver type
   CUtensorMap tma_b;
   CUtensorMap tma_d;        // 3-D (N, M, splits) fp32, box (32, 32, 1), SWIZZLE_128B
+  CUtensorMap tma_d2;       // same shape: second output of the blend epilogue (unused otherwise)
   int M, N, K;
   int bn;                   // N tile, multiple of 32, <= 256
   int splits;
@@ -58,6 +63,8 @@ struct GemmParams {
   int m_groups;             // ceil(m_tiles / cluster)
   int prefetch_a;           // 1: TMA-prefetch A tiles into L2 PREFETCH_DIST K blocks ahead
   int prefetch_b;
+  int msub;                 // 128-row sub-tiles per CTA tile (1 or 2): 2 halves the B bytes per FLOP
+  int nacc;                 // TMEM accumulator stages: 2 if 2 * msub * bn <= 512 columns, else 1
   EpiParams epi;
 };
 
@@ -249,7 +256,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
 
 // ---------------------------------------------------------------------------------------------
 // The kernel.  Dynamic smem (after 1024 B alignment):
-//   [stages] x { A tile 128 x 128 B | B tile bn x 128 B }, 8 x 4 KB epilogue boxes,
+//   [stages] x { A tile (128 * msub) x 128 B | B tile bn x 128 B }, 8 x 4 KB epilogue boxes,
 //   full[8], empty[8], tmem_full[2], tmem_empty[2] mbarriers, tmem base pointer.
 // ---------------------------------------------------------------------------------------------
 template <bool A_MN, bool B_MN>
@@ -257,7 +264,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = BM * 128u;
+  const uint32_t a_bytes = BM * 128u * static_cast<uint32_t>(p.msub);
+  const int TM = BM * p.msub;                  // rows of one CTA tile
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t epi_base = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
@@ -275,6 +283,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
     prefetch_tmap(&p.tma_a);
     prefetch_tmap(&p.tma_b);
     prefetch_tmap(&p.tma_d);
+    if (p.epi.blend_x != nullptr) prefetch_tmap(&p.tma_d2);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -318,7 +327,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
       const int nt = tile % p.n_tiles;
       const int mt = ((tile / p.n_tiles) % p.m_groups) * C + static_cast<int>(crank);
       const int z = tile / (p.n_tiles * p.m_groups);
-      const int m0 = mt * BM, n0 = nt * p.bn;
+      const int m0 = mt * TM, n0 = nt * p.bn;
       const int kb0 = z * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -338,7 +347,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
                 tma_prefetch_2d(&p.tma_a, kp0, m0);
               } else {
 #pragma unroll
-                for (int c = 0; c < BM / 32; ++c) tma_prefetch_2d(&p.tma_a, m0 + 32 * c, kp0);
+                for (int c = 0; c < TM / 32; ++c) tma_prefetch_2d(&p.tma_a, m0 + 32 * c, kp0);
               }
             }
             if (p.prefetch_b && crank == 0) {
@@ -351,10 +360,9 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           }
           mbar_expect_tx(fb, stage_bytes);
           if (!A_MN) {
-            tma_load_2d(sa, &p.tma_a, fb, k0, m0);                       // box [128 rows][32 k]
+            tma_load_2d(sa, &p.tma_a, fb, k0, m0);                       // box [128 * msub rows][32 k]
           } else {
-#pragma unroll
-            for (int c = 0; c < BM / 32; ++c)                            // boxes [32 k][32 m]
+            for (int c = 0; c < TM / 32; ++c)                            // boxes [32 k][32 m]
               tma_load_2d(sa + c * 4096, &p.tma_a, fb, m0 + 32 * c, k0);
           }
           if (C == 1) {
@@ -401,21 +409,25 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
       const int z = tile / (p.n_tiles * p.m_groups);
       const int kb0 = z * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = (p.nacc == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
       tcgen05_after_sync();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.bn);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.msub * p.bn);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar + 8 * stage, phase);
         tcgen05_after_sync();
         const uint32_t a_lo = a_lo0 + stage * stage_step;
         const uint32_t b_lo = b_lo0 + stage * stage_step;
         if (elect_one()) {
+          for (int sub = 0; sub < p.msub; ++sub) {       // both 128-row sub-tiles reuse the B tile in smem
+            const uint32_t a_sub = a_lo + sub * ((BM * 128u) >> 4);
+            const uint32_t d_sub = d_tmem + static_cast<uint32_t>(sub * p.bn);
 #pragma unroll
-          for (int s = 0; s < BK / UMMA_K; ++s)
-            umma_tf32(d_tmem, pack64(a_lo + s * a_kstep, a_hi), pack64(b_lo + s * b_kstep, b_hi), idesc,
-                      (kb > kb0 || s > 0) ? 1u : 0u);
+            for (int s = 0; s < BK / UMMA_K; ++s)
+              umma_tf32(d_sub, pack64(a_sub + s * a_kstep, a_hi), pack64(b_lo + s * b_kstep, b_hi), idesc,
+                        (kb > kb0 || s > 0) ? 1u : 0u);
+          }
           // frees the smem slot (in every CTA of the cluster: peers multicast into it) when these MMAs retire
           if (C == 1) umma_commit(empty_bar + 8 * stage);
           else umma_commit_mc(empty_bar + 8 * stage, cmask);
@@ -436,17 +448,22 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
       const int nt = tile % p.n_tiles;
       const int mt = ((tile / p.n_tiles) % p.m_groups) * C + static_cast<int>(crank);
       const int z = tile / (p.n_tiles * p.m_groups);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int row0 = mt * BM + 32 * q;
-      const int row = row0 + lane;
-      const bool row_ok = row < p.M;
+      const int acc = (p.nacc == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tcgen05_after_sync();
+      for (int sub = 0; sub < p.msub; ++sub) {
+      const int row0 = mt * TM + sub * BM + 32 * q;
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t tcol0 = static_cast<uint32_t>((acc * p.msub + sub) * p.bn);
       float rs = 1.0f;
       if (fused && e.row_scale != nullptr && row_ok) rs = __ldg(e.row_scale + row);
       const bool bias_vec = (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
       const bool aux_vec = ((reinterpret_cast<uintptr_t>(e.aux) & 15) == 0) && ((e.ld_aux & 3) == 0);
+      const bool blend = fused && e.blend_x != nullptr;
+      const bool blend_vec = ((reinterpret_cast<uintptr_t>(e.blend_x) & 15) == 0) && ((e.ld_blend & 3) == 0);
+      const float beps = (blend && row_ok) ? __ldg(e.blend_eps + row) : 0.0f;
       float sumsq = 0.0f;
       if (row0 < p.M) {
         const int nchunks = p.bn / 32;
@@ -454,8 +471,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           const int n0 = nt * p.bn + c * 32;
           if (n0 >= p.N) break;
           uint32_t v[32];
-          tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) +
-                              static_cast<uint32_t>(acc * p.bn + c * 32), v);
+          tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 +
+                              static_cast<uint32_t>(c * 32), v);
           if (fused) {
             // epilogue operands are fetched while the TMEM load is in flight
             float t[32];
@@ -514,14 +531,41 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
             tma_store_commit();
           }
           ++nstore;
+          if (blend) {
+            float t[32];
+            if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, t);
+            const float om = 1.0f - beps;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(row_ok ? beps * t[j] + om * __uint_as_float(v[j]) : 0.0f);
+            const uint32_t buf2 = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a = rb2 + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
+                           "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&p.tma_d2, buf2, n0, row0, z);
+              tma_store_commit();
+            }
+            ++nstore;
+          }
         }
       }
+      if (fused && e.row_sumsq != nullptr && row_ok)
+        e.row_sumsq[static_cast<size_t>(nt) * p.M + row] = sumsq;
+      }  // sub
       // all of this warp's TMEM reads for the tile are done: hand the accumulator back
       tcgen05_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-      if (fused && e.row_sumsq != nullptr && row_ok)
-        e.row_sumsq[static_cast<size_t>(nt) * p.M + row] = sumsq;
     }
     if (lane == 0) tma_store_wait_all();
   }

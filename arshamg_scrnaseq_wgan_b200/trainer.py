@@ -231,7 +231,7 @@ class WGANTrainer:
         self._ck(self.lib.wgan_get_scalars(self._h, net, out.ctypes.data_as(C.c_void_p), _stream()), "get_scalars")
         return out
 
-    def critic_step(self, x, z, eps=None, apply: bool = True, read: bool = True):
+    def critic_step(self, x, z, eps=None, apply: bool = True, read: bool = True, global_batch: Optional[int] = None):
         """One critic update [W:199]: gradients of obj_d (+GP), all-reduce, Adam.
         x [rows, gex], z [rows, noise], eps [rows] are this rank's shard."""
         xp, ldx, rows = self._mat(x, self.cfg.gex_size)
@@ -240,8 +240,8 @@ class WGANTrainer:
         ep = C.c_void_p(eps.data_ptr()) if eps is not None else C.c_void_p()
         if eps is not None:
             assert eps.is_cuda and eps.dtype == torch.float32 and eps.numel() == rows and eps.is_contiguous()
-        self._ck(self.lib.wgan_critic_grads(self._h, xp, ldx, zp, ldz, ep, rows, rows * self.world, _stream()),
-                 "critic_grads")
+        gb = rows * self.world if global_batch is None else int(global_batch)
+        self._ck(self.lib.wgan_critic_grads(self._h, xp, ldx, zp, ldz, ep, rows, gb, _stream()), "critic_grads")
         self._allreduce(NET_CRITIC)
         if apply:
             self._ck(self.lib.wgan_critic_apply(self._h, _stream()), "critic_apply")
@@ -251,11 +251,11 @@ class WGANTrainer:
         wass = float(s[0] - s[1])                                       # obj_d [W:137]
         return {"wasserstein": wass, "gp": float(s[2]), "critic_loss": wass + float(s[2])}
 
-    def generator_step(self, z, apply: bool = True, read: bool = True):
+    def generator_step(self, z, apply: bool = True, read: bool = True, global_batch: Optional[int] = None):
         """One generator update [W:196]: gradients of obj_g through the critic, all-reduce, Adam."""
         zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
-        self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, rows * self.world, _stream()),
-                 "generator_grads")
+        gb = rows * self.world if global_batch is None else int(global_batch)
+        self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, gb, _stream()), "generator_grads")
         self._allreduce(NET_GENERATOR)
         if apply:
             self._ck(self.lib.wgan_generator_apply(self._h, _stream()), "generator_apply")
@@ -416,6 +416,51 @@ class WGANTrainer:
             if r:
                 out.update(r)
         r = self.generator_step(self._zgen, read=read)
+        if r:
+            out.update(r)
+        return out if read else None
+
+    def train_iteration_host_indices(self, idxs, zs, epss, z_gen, read: bool = True):
+        """One WGAN-GP iteration on the RESIDENT training matrix (set_data) with the per-update host
+        inputs of the reference loop [W:188-193] fed from pinned host memory: the minibatch cell
+        indices (np.random.randint), the latent noise and the interpolation weights.  The column
+        gather of [W:189-191] happens on the device.  Copies of update k+1 overlap update k."""
+        cfg = self.cfg
+        B = idxs[0].shape[0]
+        dev = f"cuda:{self.device}"
+        if getattr(self, "_istage", None) is None or self._istage[0][0].shape[0] != B:
+            self._istage = [(torch.empty((B,), device=dev, dtype=torch.int64),
+                             torch.empty((B, cfg.noise_input_size), device=dev), torch.empty((B,), device=dev))
+                            for _ in range(2)]
+            self._izgen = torch.empty((B, cfg.noise_input_size), device=dev)
+            self._icopy = torch.cuda.Stream(device=dev)
+            self._iready = [torch.cuda.Event() for _ in range(2)]
+            self._ifree = [torch.cuda.Event() for _ in range(2)]
+            self._infeed = 0
+        main = torch.cuda.current_stream()
+        out = {}
+        n = len(idxs)
+        for k in range(n):
+            slot = self._infeed % 2
+            id_, zd, ed = self._istage[slot]
+            with torch.cuda.stream(self._icopy):
+                if self._infeed >= 2:
+                    self._icopy.wait_event(self._ifree[slot])
+                id_.copy_(idxs[k], non_blocking=True)
+                zd.copy_(zs[k], non_blocking=True)
+                if cfg.lambda_gp != 0:
+                    ed.copy_(epss[k], non_blocking=True)
+                if k == n - 1:
+                    self._izgen.copy_(z_gen, non_blocking=True)
+                self._iready[slot].record(self._icopy)
+            main.wait_event(self._iready[slot])
+            x = self.gather(id_)
+            r = self.critic_step(x, zd, ed if cfg.lambda_gp != 0 else None, read=read and k == n - 1)
+            self._ifree[slot].record(main)
+            self._infeed += 1
+            if r:
+                out.update(r)
+        r = self.generator_step(self._izgen, read=read)
         if r:
             out.update(r)
         return out if read else None

@@ -1,0 +1,72 @@
+"""Two-GPU NCCL test of the data-parallel path (skipped on boxes with fewer than 2 GPUs): each rank
+runs the real CUDA step on its batch shard, one all-reduce of the flat gradient arena per optimizer
+step; afterwards both ranks hold bit-identical parameters equal (up to summation order / TF32 mask
+flips) to a single-GPU run on the full batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+DIMS = dict(noise_input_size=20, inflate_to_size=40, gex_size=133, disc_internal_size=24)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir, mode):
+    import torch.distributed as dist
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer, PARAM_NAMES
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    B = 64
+    cfg = WGANConfig(lambda_gp=10.0, learn_rate=1e-3, **DIMS)
+    tr = WGANTrainer(cfg, max_batch=B, device=rank, gemm_mode=mode)
+    tr.init_params(seed=4)
+    g = np.random.default_rng(0)
+    x = torch.tensor(g.random((B, cfg.gex_size)), dtype=torch.float32, device=f"cuda:{rank}")
+    z = torch.tensor(np.abs(g.normal(1, 0.5, (B, cfg.noise_input_size))), dtype=torch.float32, device=f"cuda:{rank}")
+    eps = torch.tensor(g.random(B), dtype=torch.float32, device=f"cuda:{rank}")
+    sl = slice(rank * B // world, (rank + 1) * B // world)
+    for _ in range(3):
+        sc = tr.critic_step(x[sl], z[sl], eps[sl])
+        sg = tr.generator_step(z[sl])
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), scal=np.array([sc["wasserstein"], sc["gp"], sg["gen_loss"]]),
+             **{k.replace("/", "__"): tr.get_tensor(k) for k in PARAM_NAMES})
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_two_gpu_nccl_matches_single_gpu(tmp_path, mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer, PARAM_NAMES
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), mode), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    B = 64
+    cfg = WGANConfig(lambda_gp=10.0, learn_rate=1e-3, **DIMS)
+    tr = WGANTrainer(cfg, max_batch=B, device=0, gemm_mode=mode, distributed=False)
+    tr.init_params(seed=4)
+    g = np.random.default_rng(0)
+    x = torch.tensor(g.random((B, cfg.gex_size)), dtype=torch.float32, device="cuda:0")
+    z = torch.tensor(np.abs(g.normal(1, 0.5, (B, cfg.noise_input_size))), dtype=torch.float32, device="cuda:0")
+    eps = torch.tensor(g.random(B), dtype=torch.float32, device="cuda:0")
+    for _ in range(3):
+        sc = tr.critic_step(x, z, eps)
+        sg = tr.generator_step(z)
+    tol = 2e-2 if mode == 0 else 1e-4
+    assert np.allclose(r0["scal"], [sc["wasserstein"], sc["gp"], sg["gen_loss"]], rtol=tol, atol=tol * 0.1)
+    for k in PARAM_NAMES:
+        kk = k.replace("/", "__")
+        assert np.array_equal(r0[kk], r1[kk]), k                                  # replicas identical
+        ref = tr.get_tensor(k)
+        assert np.linalg.norm(r0[kk] - ref) <= tol * np.linalg.norm(ref) + 1e-7, k
