@@ -77,6 +77,7 @@ struct wgan_handle {
   int last_gx_rows;
   int gemm_cluster;                  // preferred cluster size of the tensor-core GEMM (1, 2 or 4)
   int gemm_msub;                     // 0 = auto, 1 / 2 = force 128- / 256-row CTA tiles
+  int gemm_2cta;                     // 1 = CTA-pair (cta_group::2) kernel
 
   float* P(int t) { return arena[td[t].net][WGAN_KIND_PARAM] + td[t].offset; }
   float* Gr(int t) { return arena[td[t].net][WGAN_KIND_GRAD] + td[t].offset; }
@@ -186,6 +187,20 @@ int pick_bn(int N) {
   return best;
 }
 
+// N tile of the CTA-pair kernel: cta_group::2 runs at N/2 cycles per UMMA_K step with no fixed cost, so
+// only padding and A re-reads matter; each CTA loads bn/2 columns, which must be whole 32-column boxes
+// for an MN-major B (bn % 64 == 0).
+int pick_bn_2cta(int N, bool b_mn) {
+  const int step = b_mn ? 64 : 32;
+  int best = 256;
+  long best_cost = 1L << 60;
+  for (int bn = 256; bn >= step; bn -= step) {
+    const long cost = static_cast<long>(cdiv(N, bn)) * (bn + 48);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 size_t gemm_smem_bytes(int bn, int msub, int* stages_out) {
   const size_t budget = 232448;                       // 227 KB opt-in maximum per CTA
   const size_t fixed = 1024 + EPI_BUFS * EPI_BOX_BYTES + 256;
@@ -250,6 +265,35 @@ int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int cluster_tile
   return post_launch(h, "gemm_tf32_kernel");
 }
 
+// CTA-pair kernel: cluster (2,1,1), at most num_sms/2 co-resident pairs.
+template <bool A_MN, bool B_MN>
+int launch_tc2(wgan_handle* h, const GemmParams& p, size_t smem, int pair_tiles, cudaStream_t s) {
+  static bool attr_set[16] = {};
+  int dev = h->cfg.device & 15;
+  if (!attr_set[dev]) {
+    CK(cudaFuncSetAttribute(gemm_tf32_2cta_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            232448));
+    attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int max_pairs = h->num_sms / 2;
+  const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+  cfg.gridDim = dim3(pairs * 2);
+  CK(cudaLaunchKernelEx(&cfg, gemm_tf32_2cta_kernel<A_MN, B_MN>, p));
+  return post_launch(h, "gemm_tf32_2cta_kernel");
+}
+
 // D[M,N] = epi( sum_parts A_i * B_i ).  a_mn/b_mn: operand majors (see gemm_sm100.cuh).
 int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts, float* D, int ldd,
              int M, int N, const EpiParams& epi, int* sumsq_tiles, int force_splits, cudaStream_t s,
@@ -285,28 +329,31 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     return 0;
   }
 
+  // ---- tile configuration ----
+  // two_cta: CTA pairs (tcgen05 cta_group::2) compute 256 x bn tiles, each CTA holding half of the B tile
+  // (full TF32 MMA rate, 6 smem stages).  Otherwise one CTA per 128 x bn tile (optionally 2 sub-tiles).
+  // The pair kernel is the default; a 128-row tiling is kept for outputs whose row count would be
+  // padded >10 % more by 256-row tiles (e.g. M = 600: 768 vs 640 rows).
+  const double waste2 = static_cast<double>(cdiv(M, 2 * BM)) * 2 * BM / M;
+  const double waste1 = static_cast<double>(cdiv(M, BM)) * BM / M;
+  const bool two_cta = h->gemm_2cta != 0 && waste2 <= 1.10 * waste1;
   static const int bn_cap = getenv("WGAN_B200_GEMM_BN") ? atoi(getenv("WGAN_B200_GEMM_BN")) : 0;          // experiments
-  const int bn = (bn_cap >= 32 && bn_cap % 32 == 0 && pick_bn(N) > bn_cap) ? bn_cap : pick_bn(N);
+  int bn = two_cta ? pick_bn_2cta(N, b_mn) : pick_bn(N);
+  if (!two_cta && bn_cap >= 32 && bn_cap % 32 == 0 && bn > bn_cap) bn = bn_cap;
   const int n_tiles = cdiv(N, bn);
-  // 256-row CTA tiles (two 128-row accumulators sharing the B tile in smem) halve the B bytes per
-  // FLOP; used whenever the output still has enough tiles (x possible K splits) to fill the machine
   int msub = 1;
-  {
-    int min_kb = 1 << 30;
-    for (int i = 0; i < nparts; ++i) min_kb = std::min(min_kb, cdiv(parts[i].K, BK));
-    const long units2 = static_cast<long>(cdiv(M, 2 * BM)) * n_tiles * nparts * std::max(1, min_kb / 8);
-    (void)units2;   // measured (profiles/r01_gemm_shape_sweeps.txt): 256-row tiles lose more to the shallower ring
-    if (h->gemm_msub == 2 && M >= 2 * BM) msub = 2;   // than they gain from B reuse on every WGAN shape: opt-in only
-  }
+  if (!two_cta && h->gemm_msub == 2 && M >= 2 * BM) msub = 2;   // opt-in: measured slower on every WGAN shape
   const int nacc = (2 * msub * bn <= 512) ? 2 : 1;
-  const int m_tiles = cdiv(M, BM * msub);
+  const int tile_rows = two_cta ? 2 * BM : BM * msub;
+  const int m_tiles = cdiv(M, tile_rows);
   const int tiles = m_tiles * n_tiles;
-  // CTAs of a cluster take adjacent M tiles and share the B tile through TMA multicast
-  int cluster = h->gemm_cluster;
+  const int ctas_per_tile = two_cta ? 2 : 1;
+  // (1-CTA only) CTAs of a cluster take adjacent M tiles and share the B tile through TMA multicast
+  int cluster = two_cta ? 1 : h->gemm_cluster;
   while (cluster > 1 && (m_tiles < cluster || (bn / 32) % cluster != 0)) cluster >>= 1;
   const int m_groups = cdiv(m_tiles, cluster);
   int stages;
-  const size_t smem = gemm_smem_bytes(bn, msub, &stages);
+  const size_t smem = two_cta ? gemm_smem_bytes(bn / 2, 1, &stages) : gemm_smem_bytes(bn, msub, &stages);
 
   // split-K policy: fill ~2 waves when the output has few tiles, at least 8 k-blocks per split
   int splits[2], kbps[2], total_splits = 0;
@@ -315,8 +362,8 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     int sp = 1;
     if (force_splits > 0) {
       sp = force_splits;
-    } else if (tiles * nparts * 2 <= h->num_sms) {       // at most half the SMs would have a tile
-      sp = cdiv(2 * h->num_sms, tiles * nparts);
+    } else if (tiles * nparts * ctas_per_tile * 2 <= h->num_sms) {   // at most half the SMs would have a tile
+      sp = cdiv(2 * h->num_sms, tiles * nparts * ctas_per_tile);
       if (sp > total_kb / 8) sp = total_kb / 8;
     }
     if (sp > total_kb) sp = total_kb;
@@ -341,9 +388,9 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     const Part& pt = parts[i];
     GemmParams p;
     memset(&p, 0, sizeof p);
-    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, BM * msub, false));
+    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, two_cta ? BM : BM * msub, false));
     else       TRY(make_map_2d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, 32, 32, true));
-    if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, bn / cluster, false));
+    if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, two_cta ? bn / 2 : bn / cluster, false));
     else       TRY(make_map_2d(h, &p.tma_b, pt.B, N, pt.K, pt.ldb, 32, 32, true));
     TRY(make_map_out(h, &p.tma_d, out + (direct ? 0 : slab * slab0), N, M, splits[i], ldd, slab));
     if (direct && epi.blend_x != nullptr)
@@ -368,7 +415,12 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     if (direct) p.epi = epi;
     else p.splits = splits[i];
     const int grid = m_groups * n_tiles * splits[i];       // cluster tiles; launch_tc caps at residency
-    if (!a_mn && b_mn) TRY((launch_tc<false, true>(h, p, smem, grid, s)));
+    if (two_cta) {
+      if (!a_mn && b_mn) TRY((launch_tc2<false, true>(h, p, smem, grid, s)));
+      else if (!a_mn && !b_mn) TRY((launch_tc2<false, false>(h, p, smem, grid, s)));
+      else if (a_mn && b_mn) TRY((launch_tc2<true, true>(h, p, smem, grid, s)));
+      else FAIL("gemm: A MN-major with B K-major is not instantiated");
+    } else if (!a_mn && b_mn) TRY((launch_tc<false, true>(h, p, smem, grid, s)));
     else if (!a_mn && !b_mn) TRY((launch_tc<false, false>(h, p, smem, grid, s)));
     else if (a_mn && b_mn) TRY((launch_tc<true, true>(h, p, smem, grid, s)));
     else FAIL("gemm: A MN-major with B K-major is not instantiated");
@@ -526,6 +578,8 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->launches = 0;
   h->last_gx_rows = 0;
   h->gemm_cluster = 1;
+  h->gemm_2cta = 1;
+  if (const char* env = getenv("WGAN_B200_GEMM_2CTA")) h->gemm_2cta = atoi(env) != 0;
   h->gemm_msub = 0;
   if (const char* env = getenv("WGAN_B200_GEMM_MSUB")) {
     int c = atoi(env);

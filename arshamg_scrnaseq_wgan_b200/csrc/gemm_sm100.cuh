@@ -580,4 +580,340 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   }
 }
 
+// ---- CTA-pair (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(local_bar), "r"(cta)
+      : "memory");
+}
+// data lands in this CTA's smem, the transaction bytes complete on `bar` (a shared::cluster address:
+// the pair leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant: tcgen05.mma cta_group::2, 256 x bn pair tiles (full TF32 rate: N/2 cycles per
+// UMMA_K step instead of 43 + N/2, and half the B bytes per CTA => 6 stages instead of 4).
+// ---------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // CTA pair (cta_group::2): the pair computes a 256 x bn tile; each CTA holds its 128 rows of A, HALF of
+  // the B tile (bn/2 columns) and the accumulator of its own 128 rows.  The leader (cluster rank 0) issues
+  // the MMAs for both; all loads of the pair complete on the leader's full barrier.
+  const uint32_t a_bytes = BM * 128u;
+  const int TM = 2 * BM;                       // rows of one pair tile
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn / 2) * 128u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t epi_base = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
+  const uint32_t bar_base = epi_base + EPI_BUFS * EPI_BOX_BYTES;
+  const uint32_t full_bar = bar_base;                       // 8 x 8 B
+  const uint32_t empty_bar = bar_base + 64;                 // 8 x 8 B
+  const uint32_t tfull_bar = bar_base + 128;                // 2 x 8 B
+  const uint32_t tempty_bar = bar_base + 144;               // 2 x 8 B
+  const uint32_t tmem_slot = bar_base + 160;                // 4 B
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tma_a);
+    prefetch_tmap(&p.tma_b);
+    prefetch_tmap(&p.tma_d);
+    if (p.epi.blend_x != nullptr) prefetch_tmap(&p.tma_d2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(full_bar + 8 * s, 1);
+        mbar_init(empty_bar + 8 * s, 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar + 8 * a, 1);
+        mbar_init(tempty_bar + 8 * a, 8);          // 4 epilogue warps of each CTA of the pair
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  cluster_sync_all();                          // the peer's barriers / TMEM exist before anything targets them
+  tcgen05_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  // Persistent schedule over "cluster tiles": the C CTAs of a cluster take C consecutive M tiles of
+  // the same N tile and split, and walk the K blocks in lockstep.
+  const uint32_t crank = cluster_ctarank();
+  const uint16_t cmask = 3;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;      // pair tiles
+  const int tile0 = blockIdx.x / 2, tile_step = gridDim.x / 2;
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    const uint32_t full_leader = mapa_cluster(full_bar, 0);       // all loads signal the leader's barrier
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int z = tile / (p.n_tiles * p.m_tiles);
+      const int m0 = mt * TM + static_cast<int>(crank) * BM;      // this CTA's 128 rows
+      const int n0 = nt * p.bn + static_cast<int>(crank) * (p.bn / 2);   // this CTA's half of the B tile
+      const int kb0 = z * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
+        const uint32_t fb = full_leader + 8 * stage;
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint32_t sb = sa + a_bytes;
+        const int k0 = kb * BK;
+        if (elect_one()) {
+          if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * stage_bytes);   // both CTAs' bytes
+          if (!A_MN) {
+            tma_load_2d_2sm(sa, &p.tma_a, fb, k0, m0);                   // box [128 rows][32 k]
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c)                            // boxes [32 k][32 m]
+              tma_load_2d_2sm(sa + c * 4096, &p.tma_a, fb, m0 + 32 * c, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sb, &p.tma_b, fb, k0, n0);                   // box [bn/2 rows][32 k]
+          } else {
+            for (int c = 0; c < p.bn / 64; ++c)                          // boxes [32 k][32 n]
+              tma_load_2d_2sm(sb + c * 4096, &p.tma_b, fb, n0 + 32 * c, k0);
+          }
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA only (whole warp loops, one elected lane issues) =====
+    if (crank == 0) {
+    // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                           ((B_MN ? 1u : 0u) << 16) | (static_cast<uint32_t>(p.bn >> 3) << 17) |
+                           (static_cast<uint32_t>((2 * BM) >> 4) << 24);
+    // smem descriptors: only the 14-bit start-address field changes per stage / K step
+    const uint64_t a_proto = A_MN ? make_smem_desc(0, 4096, 512, 1) : make_smem_desc(0, 16, 1024, 2);
+    const uint64_t b_proto = B_MN ? make_smem_desc(0, 4096, 512, 1) : make_smem_desc(0, 16, 1024, 2);
+    const uint32_t a_hi = static_cast<uint32_t>(a_proto >> 32), b_hi = static_cast<uint32_t>(b_proto >> 32);
+    const uint32_t a_lo0 = static_cast<uint32_t>(a_proto) | ((smem_base >> 4) & 0x3FFFu);
+    const uint32_t b_lo0 = static_cast<uint32_t>(b_proto) | (((smem_base + a_bytes) >> 4) & 0x3FFFu);
+    constexpr uint32_t a_kstep = A_MN ? (1024u >> 4) : (32u >> 4);
+    constexpr uint32_t b_kstep = B_MN ? (1024u >> 4) : (32u >> 4);
+    const uint32_t stage_step = stage_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      const int z = tile / (p.n_tiles * p.m_tiles);
+      const int kb0 = z * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
+      tcgen05_after_sync();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.bn);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tcgen05_after_sync();
+        const uint32_t a_lo = a_lo0 + stage * stage_step;
+        const uint32_t b_lo = b_lo0 + stage * stage_step;
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < BK / UMMA_K; ++s)
+            umma_tf32_2cta(d_tmem, pack64(a_lo + s * a_kstep, a_hi), pack64(b_lo + s * b_kstep, b_hi), idesc,
+                           (kb > kb0 || s > 0) ? 1u : 0u);
+          // frees the smem slot in BOTH CTAs of the pair when these MMAs retire
+          umma_commit_2cta_mc(empty_bar + 8 * stage, cmask);
+          if (kb == kb1 - 1) umma_commit_2cta_mc(tfull_bar + 8 * acc, cmask);   // accumulators complete -> both epilogues
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    }  // leader
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (TMEM -> regs -> smem -> TMA store) =====================
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const EpiParams& e = p.epi;
+    const bool fused = (p.splits == 1);
+    uint32_t nstore = 0;
+    int it = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int z = tile / (p.n_tiles * p.m_tiles);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tcgen05_after_sync();
+      {
+      const int row0 = mt * TM + static_cast<int>(crank) * BM + 32 * q;
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t tcol0 = static_cast<uint32_t>(acc * p.bn);
+      float rs = 1.0f;
+      if (fused && e.row_scale != nullptr && row_ok) rs = __ldg(e.row_scale + row);
+      const bool bias_vec = (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
+      const bool aux_vec = ((reinterpret_cast<uintptr_t>(e.aux) & 15) == 0) && ((e.ld_aux & 3) == 0);
+      const bool blend = fused && e.blend_x != nullptr;
+      const bool blend_vec = ((reinterpret_cast<uintptr_t>(e.blend_x) & 15) == 0) && ((e.ld_blend & 3) == 0);
+      const float beps = (blend && row_ok) ? __ldg(e.blend_eps + row) : 0.0f;
+      float sumsq = 0.0f;
+      if (row0 < p.M) {
+        const int nchunks = p.bn / 32;
+        for (int c = 0; c < nchunks; ++c) {
+          const int n0 = nt * p.bn + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 +
+                              static_cast<uint32_t>(c * 32), v);
+          if (fused) {
+            // epilogue operands are fetched while the TMEM load is in flight
+            float t[32];
+            if (e.bias != nullptr) {
+              load_chunk32(e.bias, n0, p.N, bias_vec, 0.0f, t);
+              tmem_ld32_wait(v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + t[j]);
+            } else {
+              tmem_ld32_wait(v);
+            }
+            if (e.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float y = __uint_as_float(v[j]);
+                v[j] = __float_as_uint(fmaxf(y, e.alpha * y));
+              }
+            }
+            if (e.aux != nullptr) {
+              if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, t);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float sl = (row_ok && !(t[j] > 0.0f)) ? e.alpha : 1.0f;
+                v[j] = __float_as_uint(__uint_as_float(v[j]) * sl);
+              }
+            }
+            if (e.row_scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
+            }
+            if (e.row_sumsq != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float y = __uint_as_float(v[j]);
+                if (n0 + j < p.N) sumsq = fmaf(y, y, sumsq);
+              }
+            }
+          } else {
+            tmem_ld32_wait(v);
+          }
+          const uint32_t buf = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
+          if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago is free again
+          __syncwarp();
+          const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = rbase + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);   // SWIZZLE_128B
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
+                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&p.tma_d, buf, n0, row0, z);
+            tma_store_commit();
+          }
+          ++nstore;
+          if (blend) {
+            float t[32];
+            if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, t);
+            const float om = 1.0f - beps;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(row_ok ? beps * t[j] + om * __uint_as_float(v[j]) : 0.0f);
+            const uint32_t buf2 = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a = rb2 + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
+                           "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&p.tma_d2, buf2, n0, row0, z);
+              tma_store_commit();
+            }
+            ++nstore;
+          }
+        }
+      }
+      if (fused && e.row_sumsq != nullptr && row_ok)
+        e.row_sumsq[static_cast<size_t>(nt) * p.M + row] = sumsq;
+      }
+      // all of this warp's TMEM reads for the tile are done: hand the accumulator back to the leader's MMA warp
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar + 8 * acc, 0);
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_before_sync();
+  __syncthreads();
+  cluster_sync_all();                          // no commit / remote arrive may target an exited CTA
+  tcgen05_after_sync();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+                 : "memory");
+  }
+}
+
 }  // namespace wg
