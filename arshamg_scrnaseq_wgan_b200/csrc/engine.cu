@@ -362,9 +362,18 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     int sp = 1;
     if (force_splits > 0) {
       sp = force_splits;
-    } else if (tiles * nparts * ctas_per_tile * 2 <= h->num_sms) {   // at most half the SMs would have a tile
-      sp = cdiv(2 * h->num_sms, tiles * nparts * ctas_per_tile);
-      if (sp > total_kb / 8) sp = total_kb / 8;
+    } else {
+      // smallest split count whose work units fill >= 85 % of the last wave of persistent CTAs (pairs),
+      // with at least 8 K blocks per split; otherwise the best-filling one
+      const int slots = h->num_sms / ctas_per_tile;
+      const int units = tiles * nparts;
+      const int max_sp = std::max(1, std::min(total_kb / 8, 64));
+      double best_eff = 0.0;
+      for (int c = 1; c <= max_sp; ++c) {
+        const double eff = static_cast<double>(units) * c / (static_cast<double>(cdiv(units * c, slots)) * slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; sp = c; }
+        if (eff >= 0.85) { sp = c; break; }
+      }
     }
     if (sp > total_kb) sp = total_kb;
     if (sp < 1) sp = 1;
@@ -776,8 +785,18 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   float* xt = h->xcat;
   float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;    // interpolates, later overwritten by gx
   // the interpolate x^ = eps x + (1 - eps) x~ is a second output of the generator-output GEMM
-  if (gp) TRY(generator_forward(h, z, lz, Bl, xt, Gl, s, x, lx, eps_dev, xh));
-  else TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
+  // (measured: the fused second output makes the epilogue the bottleneck, 125 us vs 61 + 43 us separate)
+  static const bool fuse_blend = getenv("WGAN_B200_FUSE_BLEND") != nullptr;
+  if (gp && fuse_blend) {
+    TRY(generator_forward(h, z, lz, Bl, xt, Gl, s, x, lx, eps_dev, xh));
+  } else {
+    TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
+    if (gp) {
+      blend_kernel<<<ew_grid(static_cast<size_t>(Bl) * (Gl / 4), 256, h->num_sms), 256, 0, s>>>(
+          x, lx, xt, Gl, eps_dev, xh, Gl, Bl, Gl / 4);
+      TRY(post_launch(h, "blend_kernel"));
+    }
+  }
 
   // critic layer 1 on [fake | hat | real]  [W:107-111]
   const EpiParams e1 = epi_bias_lrelu(h->P(T_B1), a);
