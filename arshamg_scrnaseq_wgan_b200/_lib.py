@@ -55,9 +55,10 @@ SIGNATURES = {
     "wgan_sample": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "wgan_critic_forward": (_I, [_P, _P, _I, _P, _I, _P]),
     "wgan_latent_fit_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _F, _P]),
-    "wgan_rng_noise_prior": (_I, [_P, _I, C.c_int64, _I, _I, _F, C.c_uint64, C.c_uint32, _P]),
-    "wgan_rng_uniform": (_I, [_P, C.c_int64, _I, C.c_uint64, C.c_uint32, _P]),
-    "wgan_rng_indices": (_I, [_P, C.c_int64, _I, C.c_uint32, C.c_uint64, C.c_uint32, _P]),
+    "wgan_rng_noise_prior": (_I, [_P, _I, C.c_int64, _I, _I, _F, C.c_uint64, C.c_uint32, _P, _P]),
+    "wgan_rng_uniform": (_I, [_P, C.c_int64, _I, C.c_uint64, C.c_uint32, _P, _P]),
+    "wgan_rng_indices": (_I, [_P, C.c_int64, _I, C.c_uint32, C.c_uint64, C.c_uint32, _P, _P]),
+    "wgan_counter_add": (_I, [_P, C.c_uint32, _P]),
     "wgan_gather_rows": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
     "wgan_gemm": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P,
                        C.POINTER(_I), _I, _P]),

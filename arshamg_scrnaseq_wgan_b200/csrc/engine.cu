@@ -1039,30 +1039,36 @@ static int upload_poisson_cdf_once() {
 }
 
 int wgan_rng_noise_prior(float* out_dev, int ld, int64_t row0, int rows, int dim, float sigma,
-                         uint64_t seed, uint32_t call_id, wgan_stream_t stream) {
+                         uint64_t seed, uint32_t call_id, const uint32_t* call_id_dev, wgan_stream_t stream) {
   if (!out_dev || rows <= 0 || dim <= 0 || ld < dim) { g_create_error = "rng_noise_prior: bad argument"; return -2; }
   if (upload_poisson_cdf_once() != 0) { g_create_error = "rng_noise_prior: constant upload failed"; return -1; }
   const size_t n = static_cast<size_t>(rows) * dim;
   int grid = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
   rng_noise_prior_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, ld, row0, rows, dim, sigma,
-                                                                               seed, call_id, 1u);
+                                                                               seed, call_id, 1u, call_id_dev);
   return rng_launch_check("rng_noise_prior_kernel");
 }
 
 int wgan_rng_uniform(float* out_dev, int64_t row0, int rows, uint64_t seed, uint32_t call_id,
-                     wgan_stream_t stream) {
+                     const uint32_t* call_id_dev, wgan_stream_t stream) {
   if (!out_dev || rows <= 0) { g_create_error = "rng_uniform: bad argument"; return -2; }
   rng_uniform_kernel<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, row0, rows, seed,
-                                                                                     call_id, 2u);
+                                                                                     call_id, 2u, call_id_dev);
   return rng_launch_check("rng_uniform_kernel");
 }
 
 int wgan_rng_indices(int64_t* out_dev, int64_t row0, int rows, uint32_t n_cells, uint64_t seed,
-                     uint32_t call_id, wgan_stream_t stream) {
+                     uint32_t call_id, const uint32_t* call_id_dev, wgan_stream_t stream) {
   if (!out_dev || rows <= 0 || n_cells == 0) { g_create_error = "rng_indices: bad argument"; return -2; }
   rng_indices_kernel<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, row0, rows, n_cells,
-                                                                                     seed, call_id, 3u);
+                                                                                     seed, call_id, 3u, call_id_dev);
   return rng_launch_check("rng_indices_kernel");
+}
+
+int wgan_counter_add(uint32_t* counter_dev, uint32_t inc, wgan_stream_t stream) {
+  if (!counter_dev) { g_create_error = "counter_add: null argument"; return -2; }
+  counter_add_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counter_dev, inc);
+  return rng_launch_check("counter_add_kernel");
 }
 
 int wgan_gather_rows(const float* data_dev, int ld_data, const int64_t* idx_dev, float* out_dev,

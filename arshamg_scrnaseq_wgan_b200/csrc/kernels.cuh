@@ -359,8 +359,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 __constant__ float c_poisson1_cdf[12];
 
 // noise_prior: |Normal(0, sigma) + Poisson(1)|  [W:91-94]; element index = global_row*dim + col.
+// In every RNG kernel the call id is `call_id + *call_id_dev` (call_id_dev may be null): the device
+// counter lets a captured CUDA graph draw fresh numbers on every replay.
 __global__ void rng_noise_prior_kernel(float* __restrict__ out, int ld, long row0, int rows, int dim,
-                                       float sigma, uint64_t seed, uint32_t call_id, uint32_t stream) {
+                                       float sigma, uint64_t seed, uint32_t call_id, uint32_t stream,
+                                       const uint32_t* __restrict__ call_id_dev) {
+  if (call_id_dev != nullptr) call_id += *call_id_dev;
   const size_t total = static_cast<size_t>(rows) * dim;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -382,7 +386,8 @@ __global__ void rng_noise_prior_kernel(float* __restrict__ out, int ld, long row
 
 // U[0,1) per global row (epsilon of the interpolates).
 __global__ void rng_uniform_kernel(float* __restrict__ out, long row0, int rows, uint64_t seed,
-                                   uint32_t call_id, uint32_t stream) {
+                                   uint32_t call_id, uint32_t stream, const uint32_t* __restrict__ call_id_dev) {
+  if (call_id_dev != nullptr) call_id += *call_id_dev;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const uint64_t idx = static_cast<uint64_t>(row0 + r);
@@ -393,13 +398,19 @@ __global__ void rng_uniform_kernel(float* __restrict__ out, long row0, int rows,
 
 // Uniform-with-replacement cell indices in [0, n_cells)  [W:188].
 __global__ void rng_indices_kernel(int64_t* __restrict__ out, long row0, int rows, uint32_t n_cells,
-                                   uint64_t seed, uint32_t call_id, uint32_t stream) {
+                                   uint64_t seed, uint32_t call_id, uint32_t stream,
+                                   const uint32_t* __restrict__ call_id_dev) {
+  if (call_id_dev != nullptr) call_id += *call_id_dev;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const uint64_t idx = static_cast<uint64_t>(row0 + r);
   const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), call_id, stream),
                                   make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
   out[r] = static_cast<int64_t>((static_cast<uint64_t>(rnd.x) * n_cells) >> 32);
+}
+
+__global__ void counter_add_kernel(uint32_t* counter, uint32_t inc) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *counter += inc;
 }
 
 // Minibatch gather from the resident cells-major matrix: out[r,:] = data[idx[r],:]  [W:188-191]

@@ -290,7 +290,7 @@ class WGANTrainer:
         return out
 
     def noise_prior(self, batch_size: int, dim: Optional[int] = None, seed: int = 0, call_id: Optional[int] = None,
-                    row0: Optional[int] = None, data_max_value: float = 1.0) -> torch.Tensor:
+                    row0: Optional[int] = None, data_max_value: float = 1.0, counter=None) -> torch.Tensor:
         """abs(Normal(0, data_max/10) + Poisson(1)) [W:91-94], drawn on the device (Philox)."""
         dim = self.cfg.noise_input_size if dim is None else dim
         if call_id is None:
@@ -300,23 +300,30 @@ class WGANTrainer:
             row0 = self.rank * batch_size
         out = torch.empty((batch_size, dim), device=f"cuda:{self.device}", dtype=torch.float32)
         rc = self.lib.wgan_rng_noise_prior(C.c_void_p(out.data_ptr()), dim, row0, batch_size, dim,
-                                           data_max_value / 10.0, seed, call_id, _stream())
+                                           data_max_value / 10.0, seed, call_id, self._cptr(counter), _stream())
         if rc != 0:
             raise _lib.WganError("rng_noise_prior: " + self.lib.wgan_last_error(None).decode())
         return out
 
-    def uniform(self, rows: int, seed: int, call_id: int, row0: Optional[int] = None) -> torch.Tensor:
+    @staticmethod
+    def _cptr(counter):
+        return C.c_void_p(counter.data_ptr()) if counter is not None else C.c_void_p()
+
+    def uniform(self, rows: int, seed: int, call_id: int, row0: Optional[int] = None, counter=None) -> torch.Tensor:
         out = torch.empty((rows,), device=f"cuda:{self.device}", dtype=torch.float32)
         row0 = self.rank * rows if row0 is None else row0
-        rc = self.lib.wgan_rng_uniform(C.c_void_p(out.data_ptr()), row0, rows, seed, call_id, _stream())
+        rc = self.lib.wgan_rng_uniform(C.c_void_p(out.data_ptr()), row0, rows, seed, call_id, self._cptr(counter),
+                                       _stream())
         if rc != 0:
             raise _lib.WganError("rng_uniform: " + self.lib.wgan_last_error(None).decode())
         return out
 
-    def indices(self, rows: int, n_cells: int, seed: int, call_id: int, row0: Optional[int] = None) -> torch.Tensor:
+    def indices(self, rows: int, n_cells: int, seed: int, call_id: int, row0: Optional[int] = None,
+                counter=None) -> torch.Tensor:
         out = torch.empty((rows,), device=f"cuda:{self.device}", dtype=torch.int64)
         row0 = self.rank * rows if row0 is None else row0
-        rc = self.lib.wgan_rng_indices(C.c_void_p(out.data_ptr()), row0, rows, n_cells, seed, call_id, _stream())
+        rc = self.lib.wgan_rng_indices(C.c_void_p(out.data_ptr()), row0, rows, n_cells, seed, call_id,
+                                       self._cptr(counter), _stream())
         if rc != 0:
             raise _lib.WganError("rng_indices: " + self.lib.wgan_last_error(None).decode())
         return out
@@ -348,32 +355,63 @@ class WGANTrainer:
             raise _lib.WganError("gather_rows: " + self.lib.wgan_last_error(None).decode())
         return out
 
-    def train_iteration_resident(self, it: int, batch: int, seed: int = 0, read: bool = False):
+    def train_iteration_resident(self, it: int, batch: int, seed: int = 0, read: bool = False, counter=None):
         """One WGAN-GP iteration with everything drawn on the device: n_critic critic updates
         (fresh minibatch, noise and epsilon each) and one generator update (canonical order),
-        or the reference-literal order when cfg.step_order == 'gen_first'."""
+        or the reference-literal order when cfg.step_order == 'gen_first'.  RNG call ids are
+        it * (n_critic + 1) + k; with `counter` (a device uint32) the base comes from the device."""
         cfg = self.cfg
         n = self._data.shape[0]
-        base = it * (cfg.n_critic + 1)
+        base = 0 if counter is not None else it * (cfg.n_critic + 1)
         out = {}
         if cfg.step_order == "gen_first":
-            z = self.noise_prior(batch, seed=seed, call_id=base)
-            x = self.gather(self.indices(batch, n, seed, base))
-            eps = self.uniform(batch, seed, base) if cfg.lambda_gp != 0 else None
+            z = self.noise_prior(batch, seed=seed, call_id=base, counter=counter)
+            x = self.gather(self.indices(batch, n, seed, base, counter=counter))
+            eps = self.uniform(batch, seed, base, counter=counter) if cfg.lambda_gp != 0 else None
             return self.train_iteration(x, z, eps, read=read)
         for k in range(cfg.n_critic):
             cid = base + k
-            z = self.noise_prior(batch, seed=seed, call_id=cid)
-            x = self.gather(self.indices(batch, n, seed, cid))
-            eps = self.uniform(batch, seed, cid) if cfg.lambda_gp != 0 else None
+            z = self.noise_prior(batch, seed=seed, call_id=cid, counter=counter)
+            x = self.gather(self.indices(batch, n, seed, cid, counter=counter))
+            eps = self.uniform(batch, seed, cid, counter=counter) if cfg.lambda_gp != 0 else None
             r = self.critic_step(x, z, eps, read=read)
             if read:
                 out.update(r)
-        z = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic)
+        z = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic, counter=counter)
         r = self.generator_step(z, read=read)
         if read:
             out.update(r)
         return out if read else None
+
+    def capture_iteration(self, batch: int, seed: int = 0, start_it: int = 0):
+        """Capture one resident-data iteration (every launch of n_critic critic updates + 1 generator
+        update, the device RNG, the gather and, in data-parallel runs, the NCCL all-reduces) into a CUDA
+        graph and return `replay()`.  The reference pays 4 session calls per iteration [W:184-199]; here a
+        replay is one graph launch, which is what makes the reference's own batch 32 fast.  The RNG call-id
+        base lives in a device counter advanced inside the graph, so every replay is the next iteration
+        (bit-identical to calling train_iteration_resident(it, ...) with it = start_it, start_it + 1, ...)."""
+        cfg = self.cfg
+        per_it = cfg.n_critic + 1 if cfg.step_order != "gen_first" else 1
+        counter = torch.full((1,), start_it * (cfg.n_critic + 1), dtype=torch.int32, device=f"cuda:{self.device}")
+        # warm-up outside capture (lazy attribute / occupancy queries, NCCL communicators), then rewind
+        side = torch.cuda.Stream(device=f"cuda:{self.device}")
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.train_iteration_resident(0, batch, seed=seed, counter=counter)
+        torch.cuda.current_stream().wait_stream(side)
+        counter += cfg.n_critic + 1            # the eager warm-up WAS iteration start_it; replays continue from there
+        torch.cuda.synchronize()
+        l0 = self.launch_count
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.train_iteration_resident(0, batch, seed=seed, counter=counter)
+            rc = self.lib.wgan_counter_add(C.c_void_p(counter.data_ptr()), cfg.n_critic + 1, _stream())
+            if rc != 0:
+                raise _lib.WganError("counter_add: " + self.lib.wgan_last_error(None).decode())
+        self._graph_keepalive = (graph, counter)
+        self.graph_launches_per_replay = self.launch_count - l0
+        _ = per_it
+        return graph.replay
 
     # ------------------------------------------------------------------ host-fed iteration (e2e)
     def train_iteration_host(self, xs, zs, epss, z_gen, read: bool = True):

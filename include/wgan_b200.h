@@ -113,13 +113,17 @@ int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_de
                          const float* x_dev, int ldx, float* loss_dev, int rows, float learn_rate,
                          wgan_stream_t stream);
 
-/* ---- device input pipeline (replaces host NumPy [W:91-94,188-193]); Philox4x32-10 ---- */
+/* ---- device input pipeline (replaces host NumPy [W:91-94,188-193]); Philox4x32-10 ----
+ * The draw is a pure function of (seed, call id, global row, column).  The effective call id is
+ * call_id + *call_id_dev (call_id_dev may be NULL): a device-resident counter, advanced by
+ * wgan_counter_add, lets a captured CUDA graph draw fresh numbers on every replay. */
 int wgan_rng_noise_prior(float* out_dev, int ld, int64_t row0, int rows, int dim, float sigma,
-                         uint64_t seed, uint32_t call_id, wgan_stream_t stream);
+                         uint64_t seed, uint32_t call_id, const uint32_t* call_id_dev, wgan_stream_t stream);
 int wgan_rng_uniform(float* out_dev, int64_t row0, int rows, uint64_t seed, uint32_t call_id,
-                     wgan_stream_t stream);
+                     const uint32_t* call_id_dev, wgan_stream_t stream);
 int wgan_rng_indices(int64_t* out_dev, int64_t row0, int rows, uint32_t n_cells, uint64_t seed,
-                     uint32_t call_id, wgan_stream_t stream);
+                     uint32_t call_id, const uint32_t* call_id_dev, wgan_stream_t stream);
+int wgan_counter_add(uint32_t* counter_dev, uint32_t inc, wgan_stream_t stream);
 int wgan_gather_rows(const float* data_dev, int ld_data, const int64_t* idx_dev, float* out_dev,
                      int ld_out, int rows, int cols, wgan_stream_t stream);
 

@@ -301,3 +301,32 @@ def test_shard_linearity_at_stress_batch():
     assert abs((sc[0] - sc[1]) - s_full["wasserstein"]) < 1e-3 * (abs(sc[0]) + abs(sc[1]))
     assert abs(sc[2] - s_full["gp"]) < 5e-3 * abs(s_full["gp"])
     assert np.isfinite(full.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("lit", [False, True])
+def test_cuda_graph_replay_is_bit_identical(lit):
+    """capture_iteration: a replay is the next resident-data iteration, bit for bit (same kernels, same
+    Philox call ids drawn from the device counter)."""
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer
+    B = 32
+    mk = (lambda: WGANConfig.reference_literal(learn_rate=1e-3, **SMALL)) if lit else \
+         (lambda: WGANConfig(learn_rate=1e-3, n_critic=2, **SMALL))
+    data = torch.rand((300, SMALL["gex_size"]), device="cuda:0")
+    outs = []
+    for use_graph in (False, True):
+        tr = WGANTrainer(mk(), max_batch=B, device=0)
+        tr.init_params(seed=9)
+        tr.set_data(data)
+        if use_graph:
+            replay = tr.capture_iteration(B, seed=3, start_it=0)      # runs iteration 0 eagerly
+            for _ in range(3):
+                replay()
+            assert tr.graph_launches_per_replay > 10
+        else:
+            for it in range(4):
+                tr.train_iteration_resident(it, B, seed=3)
+        torch.cuda.synchronize()
+        outs.append(tr.get_params())
+        tr.close()
+    for k in O.PARAM_NAMES:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
