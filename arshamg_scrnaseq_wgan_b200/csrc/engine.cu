@@ -153,8 +153,28 @@ int make_map_2d(wgan_handle* h, CUtensorMap* m, const float* ptr, uint64_t inner
                          const_cast<float*>(ptr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(2d) failed with %d", (int)r);
+  return 0;
+}
+
+// MN-major operand [K rows, MN cols] (MN contiguous) as a 3-D map (32 floats, K, ceil(MN/32) chunks) with
+// strides (ld, 32 floats): one box of (32, 32, chunks_per_box) lands as the [chunk][k][32] smem tile.  The last
+// chunk of a row may read up to 124 B past column MN (its results are clipped by the store); every
+// device buffer of the engine carries that slack.
+int make_map_mn3d(wgan_handle* h, CUtensorMap* m, const float* ptr, uint64_t mn, uint64_t k, uint64_t ld_floats,
+                  uint32_t chunks_per_box) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld_floats & 3) != 0)
+    FAIL("TMA operand must be 16-byte aligned with ld %% 4 == 0 (ptr=%p ld=%llu)", (const void*)ptr,
+         (unsigned long long)ld_floats);
+  cuuint64_t dims[3] = {32, k, (mn + 31) / 32};
+  cuuint64_t strides[2] = {ld_floats * 4, 128};
+  cuuint32_t box[3] = {32, 32, chunks_per_box};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(3d MN-major) failed with %d", (int)r);
   return 0;
 }
 
@@ -219,6 +239,10 @@ int launch_finish(wgan_handle* h, const float* part, size_t slab, int splits, fl
                   const EpiParams& epi, cudaStream_t s) {
   if (epi.row_sumsq == nullptr) {
     const size_t n = static_cast<size_t>(M) * ((N + 3) / 4);
+    if (splits >= 8 && n <= static_cast<size_t>(h->num_sms) * 32 * 16) {
+      finish_splitk_tall_kernel<<<static_cast<int>((n + 31) / 32), 256, 0, s>>>(part, slab, splits, D, ldd, M, N, epi);
+      return post_launch(h, "finish_splitk_tall_kernel");
+    }
     finish_splitk_vec4_kernel<<<ew_grid(n, 256, h->num_sms), 256, 0, s>>>(part, slab, splits, D, ldd, M, N, epi);
     return post_launch(h, "finish_splitk_vec4_kernel");
   }
@@ -398,9 +422,9 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     GemmParams p;
     memset(&p, 0, sizeof p);
     if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, two_cta ? BM : BM * msub, false));
-    else       TRY(make_map_2d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, 32, 32, true));
+    else       TRY(make_map_mn3d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, two_cta ? BM / 32 : BM * msub / 32));
     if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, two_cta ? bn / 2 : bn / cluster, false));
-    else       TRY(make_map_2d(h, &p.tma_b, pt.B, N, pt.K, pt.ldb, 32, 32, true));
+    else       TRY(make_map_mn3d(h, &p.tma_b, pt.B, N, pt.K, pt.ldb, two_cta ? bn / 64 : bn / 32 / cluster));
     TRY(make_map_out(h, &p.tma_d, out + (direct ? 0 : slab * slab0), N, M, splits[i], ldd, slab));
     if (direct && epi.blend_x != nullptr)
       TRY(make_map_out(h, &p.tma_d2, blend_out, N, M, 1, ldd, slab));
@@ -439,7 +463,7 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     TRY(launch_finish(h, h->splitws, slab, total_splits, D, ldd, M, N, epi, s));
     if (sumsq_tiles) *sumsq_tiles = 1;
   } else if (sumsq_tiles) {
-    *sumsq_tiles = n_tiles;
+    *sumsq_tiles = n_tiles * (NUM_EPI_WARPS / 4);
   }
   return 0;
 }
@@ -666,7 +690,7 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
 
   // ---- workspace ----
   const size_t R = h->R;
-  h->nsq_tiles_max = cdiv(h->G, 32);
+  h->nsq_tiles_max = cdiv(h->G, 32) * (NUM_EPI_WARPS / 4);
   h->colpart_stride = 64 * (h->G > h->Hg ? (h->G > h->Hd ? h->G : h->Hd) : (h->Hg > h->Hd ? h->Hg : h->Hd));
   struct { float** p; size_t n; } allocs[] = {
       {&h->zbuf, R * h->Zl}, {&h->gh1, R * h->Hgl}, {&h->gh2, R * h->Hgl}, {&h->xcat, 3 * R * h->Gl},

@@ -26,17 +26,18 @@ namespace wg {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 32;           // 32 tf32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;        // 32 B / sizeof(tf32)
-constexpr int GEMM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 4;                    // 4 or 8 (8: two warps per TMEM lane quadrant alternate chunks; measured: no gain)
+constexpr int GEMM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_BOX_BYTES = 32 * 32 * 4;   // one [32 rows][32 cols] fp32 staging box
-constexpr int EPI_BUFS = 8;                   // 4 epilogue warps x 2
+constexpr int EPI_BUFS = 2 * NUM_EPI_WARPS;    // two staging boxes per epilogue warp
 constexpr int PREFETCH_DIST = 12;             // K blocks between the L2 prefetch and the smem load
 
 struct EpiParams {
   const float* bias;        // [N] or nullptr
   const float* aux;         // [M, ld_aux] post-activation whose sign picks the LeakyReLU slope, or nullptr
   const float* row_scale;   // [M] or nullptr
-  float* row_sumsq;         // [n_tiles, M] partial sums of y^2 per N tile, or nullptr
+  float* row_sumsq;         // [n_tiles * NUM_EPI_WARPS / 4, M] partial sums of y^2, or nullptr
   int ld_aux;
   int act;                  // 0 = identity, 1 = LeakyReLU(alpha)
   float alpha;
@@ -113,6 +114,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// MN-major operands are described by a 3-D map (32 floats, K rows, MN/32 chunks) so that ONE box of
+// (32, 32, chunks) fills the whole [chunk][k][32] smem tile: 4 KB boxes cap the TMA engine at ~31 B/clk/SM,
+// 32 KB boxes reach ~51 B/clk/SM (scripts/ubench/tma_rate.cu).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                                int c0, int c1, uint16_t cta_mask) {
   asm volatile(
@@ -141,10 +160,23 @@ __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
                : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -293,7 +325,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar + 8 * a, 1);
-        mbar_init(tempty_bar + 8 * a, 4);
+        mbar_init(tempty_bar + 8 * a, NUM_EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -347,14 +379,14 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
                 tma_prefetch_2d(&p.tma_a, kp0, m0);
               } else {
 #pragma unroll
-                for (int c = 0; c < TM / 32; ++c) tma_prefetch_2d(&p.tma_a, m0 + 32 * c, kp0);
+                tma_prefetch_3d(&p.tma_a, 0, kp0, m0 / 32);
               }
             }
             if (p.prefetch_b && crank == 0) {
               if (!B_MN) {
                 for (int r = 0; r < C; ++r) tma_prefetch_2d(&p.tma_b, kp0, n0 + r * (p.bn / C));
               } else {
-                for (int c = 0; c < p.bn / 32; ++c) tma_prefetch_2d(&p.tma_b, n0 + 32 * c, kp0);
+                tma_prefetch_3d(&p.tma_b, 0, kp0, n0 / 32);
               }
             }
           }
@@ -362,15 +394,13 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           if (!A_MN) {
             tma_load_2d(sa, &p.tma_a, fb, k0, m0);                       // box [128 * msub rows][32 k]
           } else {
-            for (int c = 0; c < TM / 32; ++c)                            // boxes [32 k][32 m]
-              tma_load_2d(sa + c * 4096, &p.tma_a, fb, m0 + 32 * c, k0);
+            tma_load_3d(sa, &p.tma_a, fb, 0, k0, m0 / 32);               // box [TM/32 chunks][32 k][32 m]
           }
           if (C == 1) {
             if (!B_MN) {
               tma_load_2d(sb, &p.tma_b, fb, k0, n0);                     // box [bn rows][32 k]
             } else {
-              for (int c = 0; c < p.bn / 32; ++c)                        // boxes [32 k][32 n]
-                tma_load_2d(sb + c * 4096, &p.tma_b, fb, n0 + 32 * c, k0);
+              tma_load_3d(sb, &p.tma_b, fb, 0, k0, n0 / 32);             // box [bn/32 chunks][32 k][32 n]
             }
           } else {
             // every CTA fetches 1/C of the shared B tile and multicasts it to the whole cluster
@@ -378,8 +408,9 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
               const int rows_per = p.bn / C;                             // tma_b box = [bn/C rows][32 k]
               tma_load_2d_mc(sb + crank * rows_per * 128, &p.tma_b, fb, k0, n0 + crank * rows_per, cmask);
             } else {
-              for (int c = crank; c < p.bn / 32; c += C)
-                tma_load_2d_mc(sb + c * 4096, &p.tma_b, fb, n0 + 32 * c, k0, cmask);
+              // (cluster multicast is an opt-in experiment: B map box = bn/32/C chunks)
+              const int cpc = p.bn / 32 / C;
+              tma_load_3d_mc(sb + crank * cpc * 4096, &p.tma_b, fb, 0, k0, n0 / 32 + crank * cpc, cmask);
             }
           }
         }
@@ -440,6 +471,9 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   } else {
     // ===================== epilogue warps (TMEM -> regs -> smem -> TMA store) =====================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int ew = warp - 2;                       // epilogue warp index 0..NUM_EPI_WARPS-1
+    const int cpart = ew >> 2;                     // which share of the tile's 32-column chunks this warp drains
+    constexpr int CPARTS = NUM_EPI_WARPS / 4;
     const EpiParams& e = p.epi;
     const bool fused = (p.splits == 1);
     uint32_t nstore = 0;
@@ -467,7 +501,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
       float sumsq = 0.0f;
       if (row0 < p.M) {
         const int nchunks = p.bn / 32;
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = cpart; c < nchunks; c += CPARTS) {
           const int n0 = nt * p.bn + c * 32;
           if (n0 >= p.N) break;
           uint32_t v[32];
@@ -513,7 +547,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           } else {
             tmem_ld32_wait(v);
           }
-          const uint32_t buf = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
+          const uint32_t buf = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
           if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago is free again
           __syncwarp();
           const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
@@ -538,7 +572,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               v[j] = __float_as_uint(row_ok ? beps * t[j] + om * __uint_as_float(v[j]) : 0.0f);
-            const uint32_t buf2 = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
+            const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
             const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
@@ -560,7 +594,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
         }
       }
       if (fused && e.row_sumsq != nullptr && row_ok)
-        e.row_sumsq[static_cast<size_t>(nt) * p.M + row] = sumsq;
+        e.row_sumsq[static_cast<size_t>(nt * CPARTS + cpart) * p.M + row] = sumsq;
       }  // sub
       // all of this warp's TMEM reads for the tile are done: hand the accumulator back
       tcgen05_before_sync();
@@ -662,7 +696,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar + 8 * a, 1);
-        mbar_init(tempty_bar + 8 * a, 8);          // 4 epilogue warps of each CTA of the pair
+        mbar_init(tempty_bar + 8 * a, 2 * NUM_EPI_WARPS);   // the epilogue warps of both CTAs of the pair
       }
       fence_barrier_init();
     }
@@ -710,15 +744,12 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
           if (!A_MN) {
             tma_load_2d_2sm(sa, &p.tma_a, fb, k0, m0);                   // box [128 rows][32 k]
           } else {
-#pragma unroll
-            for (int c = 0; c < BM / 32; ++c)                            // boxes [32 k][32 m]
-              tma_load_2d_2sm(sa + c * 4096, &p.tma_a, fb, m0 + 32 * c, k0);
+            tma_load_3d_2sm(sa, &p.tma_a, fb, 0, k0, m0 / 32);           // box [4 chunks][32 k][32 m]
           }
           if (!B_MN) {
             tma_load_2d_2sm(sb, &p.tma_b, fb, k0, n0);                   // box [bn/2 rows][32 k]
           } else {
-            for (int c = 0; c < p.bn / 64; ++c)                          // boxes [32 k][32 n]
-              tma_load_2d_2sm(sb + c * 4096, &p.tma_b, fb, n0 + 32 * c, k0);
+            tma_load_3d_2sm(sb, &p.tma_b, fb, 0, k0, n0 / 32);           // box [bn/64 chunks][32 k][32 n]
           }
         }
         __syncwarp();
@@ -776,6 +807,9 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
   } else {
     // ===================== epilogue warps (TMEM -> regs -> smem -> TMA store) =====================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int ew = warp - 2;                       // epilogue warp index 0..NUM_EPI_WARPS-1
+    const int cpart = ew >> 2;                     // which share of the tile's 32-column chunks this warp drains
+    constexpr int CPARTS = NUM_EPI_WARPS / 4;
     const EpiParams& e = p.epi;
     const bool fused = (p.splits == 1);
     uint32_t nstore = 0;
@@ -803,7 +837,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
       float sumsq = 0.0f;
       if (row0 < p.M) {
         const int nchunks = p.bn / 32;
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = cpart; c < nchunks; c += CPARTS) {
           const int n0 = nt * p.bn + c * 32;
           if (n0 >= p.N) break;
           uint32_t v[32];
@@ -849,7 +883,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
           } else {
             tmem_ld32_wait(v);
           }
-          const uint32_t buf = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
+          const uint32_t buf = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
           if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago is free again
           __syncwarp();
           const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
@@ -874,7 +908,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               v[j] = __float_as_uint(row_ok ? beps * t[j] + om * __uint_as_float(v[j]) : 0.0f);
-            const uint32_t buf2 = epi_base + static_cast<uint32_t>((q * 2 + (nstore & 1)) * EPI_BOX_BYTES);
+            const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
             const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
@@ -896,7 +930,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
         }
       }
       if (fused && e.row_sumsq != nullptr && row_ok)
-        e.row_sumsq[static_cast<size_t>(nt) * p.M + row] = sumsq;
+        e.row_sumsq[static_cast<size_t>(nt * CPARTS + cpart) * p.M + row] = sumsq;
       }
       // all of this warp's TMEM reads for the tile are done: hand the accumulator back to the leader's MMA warp
       tcgen05_before_sync();

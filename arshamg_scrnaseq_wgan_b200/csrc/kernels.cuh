@@ -82,6 +82,58 @@ __global__ void finish_splitk_vec4_kernel(const float* __restrict__ part, size_t
   }
 }
 
+// Small outputs with many splits (K = batch weight gradients of the 200 x 200 layers): 8 warps of a
+// block each sum every 8th slab of the same 32 float4 groups, then reduce through shared memory
+// (fixed order: deterministic).
+__global__ void __launch_bounds__(256)
+finish_splitk_tall_kernel(const float* __restrict__ part, size_t slab_stride, int splits, float* out, int ld,
+                          int M, int N, EpiParams e) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n4 = (N + 3) >> 2;
+  const size_t total = static_cast<size_t>(M) * n4;
+  const size_t i = static_cast<size_t>(blockIdx.x) * 32 + lane;
+  float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+  int row = 0, n = 0;
+  size_t off = 0;
+  if (i < total) {
+    row = static_cast<int>(i / n4);
+    n = static_cast<int>(i % n4) * 4;
+    off = static_cast<size_t>(row) * ld + n;
+    for (int s = w; s < splits; s += 8) {
+      const float4 t = *reinterpret_cast<const float4*>(part + s * slab_stride + off);
+      y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
+    }
+  }
+  red[w][lane] = y;
+  __syncthreads();
+  if (w == 0 && i < total) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 t = red[k][lane];
+      y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
+    }
+    float v[4] = {y.x, y.y, y.z, y.w};
+    const float rs = e.row_scale ? e.row_scale[row] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j >= N) { v[j] = 0.0f; continue; }
+      if (e.bias) v[j] += e.bias[n + j];
+      if (e.act == 1) v[j] = fmaxf(v[j], e.alpha * v[j]);
+      if (e.aux) {
+        const float h = e.aux[static_cast<size_t>(row) * e.ld_aux + n + j];
+        v[j] *= (h > 0.0f) ? 1.0f : e.alpha;
+      }
+      v[j] *= rs;
+    }
+    if (n + 4 <= N) {
+      *reinterpret_cast<float4*>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int j = 0; n + j < N; ++j) out[off + j] = v[j];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP32 CUDA-core GEMM (verification mode only: separates algorithm bugs from TF32 rounding).
 // C[m,n] = sum_k A(m,k) B(n,k), element (m,k) of A at A[m*sam + k*sak], same for B.

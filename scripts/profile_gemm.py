@@ -27,7 +27,7 @@ if which == "genout":
     fn = lambda: gemm(0, 1, A, W, D, B, G, Hg, bias, 1)
 elif which == "gx":
     A = torch.rand((B, Hd), device=dev); W = torch.rand((G, Hd), device=dev) - 0.5
-    D = torch.empty((B, Gl), device=dev); sq = torch.empty((64 * B,), device=dev)
+    D = torch.empty((B, Gl), device=dev); sq = torch.empty((128 * B,), device=dev)
     fn = lambda: gemm(0, 0, A, W, D, B, G, Hd, sumsq=sq)
 elif which == "l1":
     A = torch.rand((3 * B, Gl), device=dev); W = torch.rand((G, Hd), device=dev) - 0.5

@@ -55,7 +55,7 @@ def _run(tr, layout, M, N, K, rng, bias=False, act=0, aux=False, row_scale=False
         rs_d = torch.tensor(s, device=dev)
         ref = ref * s[:, None]
     if sumsq:
-        sq_d = torch.zeros((64 * M,), device=dev)
+        sq_d = torch.zeros((128 * M,), device=dev)
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
     tiles = C.c_int(0)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
