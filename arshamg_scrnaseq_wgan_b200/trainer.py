@@ -413,6 +413,29 @@ class WGANTrainer:
         _ = per_it
         return graph.replay
 
+    # ------------------------------------------------------------------ bulk sampling (BASELINE config 5)
+    def sample_cells(self, n_cells: int, chunk: Optional[int] = None, seed: int = 0, sink=None,
+                     first_row: Optional[int] = None) -> Optional[torch.Tensor]:
+        """Generate n_cells cells in chunks of <= max_batch rows: z ~ noise_prior on the device, G(z).
+        The latent of global cell r is a pure function of (seed, r), so the result is independent of the
+        chunking and ranks shard the cell range without communication (rank k takes rows
+        [k * n_cells, (k + 1) * n_cells) unless first_row is given).  `sink(row0, cells)` receives every chunk
+        (e.g. to copy to host / disk); without a sink the cells are returned as one [n_cells, gex] tensor."""
+        chunk = min(chunk or self.max_batch, self.max_batch)
+        base = self.rank * n_cells if first_row is None else first_row
+        out = None
+        if sink is None:
+            out = torch.empty((n_cells, self.Gl), device=f"cuda:{self.device}", dtype=torch.float32)
+        buf = None if sink is None else torch.empty((chunk, self.Gl), device=f"cuda:{self.device}", dtype=torch.float32)
+        for r0 in range(0, n_cells, chunk):
+            n = min(chunk, n_cells - r0)
+            z = self.noise_prior(n, seed=seed, call_id=0x5A3D0000, row0=base + r0)
+            dst = (out[r0:r0 + n] if sink is None else buf[:n])[:, :self.cfg.gex_size]
+            self.generator(z, out=dst)
+            if sink is not None:
+                sink(base + r0, dst)
+        return None if sink is not None else out[:, :self.cfg.gex_size]
+
     # ------------------------------------------------------------------ host-fed iteration (e2e)
     def train_iteration_host(self, xs, zs, epss, z_gen, read: bool = True):
         """One WGAN-GP iteration fed from HOST float32 buffers, the way the reference feeds
