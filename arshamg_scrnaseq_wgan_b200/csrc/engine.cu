@@ -221,9 +221,9 @@ int pick_bn_2cta(int N, bool b_mn) {
   return best;
 }
 
-size_t gemm_smem_bytes(int bn, int msub, int* stages_out) {
+size_t gemm_smem_bytes(int bn, int msub, int* stages_out, bool side = false) {
   const size_t budget = 232448;                       // 227 KB opt-in maximum per CTA
-  const size_t fixed = 1024 + EPI_BUFS * EPI_BOX_BYTES + 256;
+  const size_t fixed = 1024 + (side ? 2 : 1) * EPI_BUFS * EPI_BOX_BYTES + 512;
   const size_t stage = static_cast<size_t>(BM) * msub * 128 + static_cast<size_t>(bn) * 128;
   int stages = static_cast<int>((budget - fixed) / stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -376,8 +376,14 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   int cluster = two_cta ? 1 : h->gemm_cluster;
   while (cluster > 1 && (m_tiles < cluster || (bn / 32) % cluster != 0)) cluster >>= 1;
   const int m_groups = cdiv(m_tiles, cluster);
+  // the epilogue's [M, N] side operand (slope-mask source / blend x) is staged by TMA when it is TMA-legal
+  const float* side_ptr = epi.aux != nullptr ? epi.aux : epi.blend_x;
+  const int side_ld = epi.aux != nullptr ? epi.ld_aux : epi.ld_blend;
+  static const bool no_side = getenv("WGAN_B200_NO_SIDE_TMA") != nullptr;
+  bool side = !no_side && side_ptr != nullptr && !(epi.aux != nullptr && epi.blend_x != nullptr) &&
+              (reinterpret_cast<uintptr_t>(side_ptr) & 15) == 0 && (side_ld & 3) == 0;
   int stages;
-  const size_t smem = two_cta ? gemm_smem_bytes(bn / 2, 1, &stages) : gemm_smem_bytes(bn, msub, &stages);
+  size_t smem = two_cta ? gemm_smem_bytes(bn / 2, 1, &stages, side) : gemm_smem_bytes(bn, msub, &stages, side);
 
   // split-K policy: fill ~2 waves when the output has few tiles, at least 8 k-blocks per split
   int splits[2], kbps[2], total_splits = 0;
@@ -415,6 +421,10 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   }
   const bool direct = (total_splits == 1);
   float* out = direct ? D : h->splitws;
+  if (!direct && side) {                               // split partials skip the fused epilogue: no side ring
+    side = false;
+    smem = two_cta ? gemm_smem_bytes(bn / 2, 1, &stages, false) : gemm_smem_bytes(bn, msub, &stages, false);
+  }
 
   int slab0 = 0;
   for (int i = 0; i < nparts; ++i) {
@@ -428,6 +438,17 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     TRY(make_map_out(h, &p.tma_d, out + (direct ? 0 : slab * slab0), N, M, splits[i], ldd, slab));
     if (direct && epi.blend_x != nullptr)
       TRY(make_map_out(h, &p.tma_d2, blend_out, N, M, 1, ldd, slab));
+    if (side) {
+      cuuint64_t sdims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M)};
+      cuuint64_t sstr[1] = {static_cast<cuuint64_t>(side_ld) * 4};
+      cuuint32_t sbox[2] = {32, 32};
+      cuuint32_t sone[2] = {1, 1};
+      CUresult r = h->encode(&p.tma_side, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(side_ptr), sdims, sstr,
+                             sbox, sone, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(side operand) failed with %d", (int)r);
+    }
+    p.side_mode = side ? 1 : 0;
     p.M = M; p.N = N; p.K = pt.K;
     p.bn = bn;
     p.splits = direct ? 1 : splits[i];
@@ -810,7 +831,7 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;    // interpolates, later overwritten by gx
   // the interpolate x^ = eps x + (1 - eps) x~ is a second output of the generator-output GEMM
   // (measured: the fused second output makes the epilogue the bottleneck, 125 us vs 61 + 43 us separate)
-  static const bool fuse_blend = getenv("WGAN_B200_FUSE_BLEND") != nullptr;
+  static const bool fuse_blend = getenv("WGAN_B200_NO_FUSE_BLEND") == nullptr;
   if (gp && fuse_blend) {
     TRY(generator_forward(h, z, lz, Bl, xt, Gl, s, x, lx, eps_dev, xh));
   } else {

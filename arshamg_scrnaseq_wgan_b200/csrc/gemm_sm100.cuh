@@ -53,6 +53,8 @@ struct GemmParams {
   CUtensorMap tma_b;
   CUtensorMap tma_d;        // 3-D (N, M, splits) fp32, box (32, 32, 1), SWIZZLE_128B
   CUtensorMap tma_d2;       // same shape: second output of the blend epilogue (unused otherwise)
+  CUtensorMap tma_side;     // 2-D (N, M) fp32, box (32, 32), SWIZZLE_128B: the epilogue's [M, N] side operand
+                            // (slope-mask source or blend x) staged through smem by TMA when side_mode != 0
   int M, N, K;
   int bn;                   // N tile, multiple of 32, <= 256
   int splits;
@@ -64,6 +66,7 @@ struct GemmParams {
   int m_groups;             // ceil(m_tiles / cluster)
   int prefetch_a;           // 1: TMA-prefetch A tiles into L2 PREFETCH_DIST K blocks ahead
   int prefetch_b;
+  int side_mode;            // 0: side operand (if any) read with per-thread global loads; 1: TMA-staged
   int msub;                 // 128-row sub-tiles per CTA tile (1 or 2): 2 halves the B bytes per FLOP
   int nacc;                 // TMEM accumulator stages: 2 if 2 * msub * bn <= 512 columns, else 1
   EpiParams epi;
@@ -301,12 +304,14 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t epi_base = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
-  const uint32_t bar_base = epi_base + EPI_BUFS * EPI_BOX_BYTES;
+  const uint32_t side_base = epi_base + EPI_BUFS * EPI_BOX_BYTES;             // 2 side boxes per epilogue warp
+  const uint32_t bar_base = side_base + (p.side_mode ? EPI_BUFS * EPI_BOX_BYTES : 0);
   const uint32_t full_bar = bar_base;                       // 8 x 8 B
   const uint32_t empty_bar = bar_base + 64;                 // 8 x 8 B
   const uint32_t tfull_bar = bar_base + 128;                // 2 x 8 B
   const uint32_t tempty_bar = bar_base + 144;               // 2 x 8 B
   const uint32_t tmem_slot = bar_base + 160;                // 4 B
+  const uint32_t side_bar = bar_base + 176;                 // EPI_BUFS x 8 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -316,6 +321,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
     prefetch_tmap(&p.tma_b);
     prefetch_tmap(&p.tma_d);
     if (p.epi.blend_x != nullptr) prefetch_tmap(&p.tma_d2);
+    if (p.side_mode) prefetch_tmap(&p.tma_side);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -323,6 +329,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
         mbar_init(full_bar + 8 * s, 1);
         mbar_init(empty_bar + 8 * s, static_cast<uint32_t>(p.cluster));   // one commit per cluster CTA
       }
+      for (int i = 0; i < EPI_BUFS; ++i) mbar_init(side_bar + 8 * i, 1);
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar + 8 * a, 1);
         mbar_init(tempty_bar + 8 * a, NUM_EPI_WARPS);
@@ -477,6 +484,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
     const EpiParams& e = p.epi;
     const bool fused = (p.splits == 1);
     uint32_t nstore = 0;
+    uint32_t side_issued = 0, side_waited = 0;     // per-warp ring of 2 TMA-staged side boxes
+    const bool side = (p.splits == 1) && p.side_mode != 0;
     int it = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int nt = tile % p.n_tiles;
@@ -501,9 +510,29 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
       float sumsq = 0.0f;
       if (row0 < p.M) {
         const int nchunks = p.bn / 32;
+        if (side && nt * p.bn + cpart * 32 < p.N && cpart < nchunks) {   // side box of this warp's first chunk
+          if (lane == 0) {
+            const uint32_t sl = ew * 2 + (side_issued & 1);
+            mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
+            tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cpart * 32, row0);
+          }
+          ++side_issued;
+        }
         for (int c = cpart; c < nchunks; c += CPARTS) {
           const int n0 = nt * p.bn + c * 32;
           if (n0 >= p.N) break;
+          float sv[32];                              // TMA-staged side operand of this chunk
+          if (side) {
+            const int cn = c + CPARTS;               // prefetch the next chunk's box into the other slot
+            if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
+              if (lane == 0) {
+                const uint32_t sl = ew * 2 + (side_issued & 1);
+                mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
+                tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cn * 32, row0);
+              }
+              ++side_issued;
+            }
+          }
           uint32_t v[32];
           tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 +
                               static_cast<uint32_t>(c * 32), v);
@@ -525,11 +554,30 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
                 v[j] = __float_as_uint(fmaxf(y, e.alpha * y));
               }
             }
+            if (side) {
+              const uint32_t sl = ew * 2 + (side_waited & 1);
+              mbar_wait(side_bar + 8 * sl, (side_waited >> 1) & 1);
+              ++side_waited;
+              const uint32_t sb = side_base + sl * EPI_BOX_BYTES + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint32_t r0, r1, r2, r3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                             : "r"(sb + (static_cast<uint32_t>(j ^ (lane & 7)) << 4))
+                             : "memory");
+                sv[4 * j] = __uint_as_float(r0); sv[4 * j + 1] = __uint_as_float(r1);
+                sv[4 * j + 2] = __uint_as_float(r2); sv[4 * j + 3] = __uint_as_float(r3);
+              }
+              __syncwarp();                          // the slot may be refilled two issues later
+            }
             if (e.aux != nullptr) {
-              if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, t);
+              if (!side) {
+                if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, sv);
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float sl = (row_ok && !(t[j] > 0.0f)) ? e.alpha : 1.0f;
+                const float sl = (row_ok && !(sv[j] > 0.0f)) ? e.alpha : 1.0f;
                 v[j] = __float_as_uint(__uint_as_float(v[j]) * sl);
               }
             }
@@ -566,12 +614,13 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           }
           ++nstore;
           if (blend) {
-            float t[32];
-            if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, t);
+            if (!side) {
+              if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, sv);
+            }
             const float om = 1.0f - beps;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              v[j] = __float_as_uint(row_ok ? beps * t[j] + om * __uint_as_float(v[j]) : 0.0f);
+              v[j] = __float_as_uint(row_ok ? beps * sv[j] + om * __uint_as_float(v[j]) : 0.0f);
             const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
@@ -672,12 +721,14 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn / 2) * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t epi_base = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
-  const uint32_t bar_base = epi_base + EPI_BUFS * EPI_BOX_BYTES;
+  const uint32_t side_base = epi_base + EPI_BUFS * EPI_BOX_BYTES;             // 2 side boxes per epilogue warp
+  const uint32_t bar_base = side_base + (p.side_mode ? EPI_BUFS * EPI_BOX_BYTES : 0);
   const uint32_t full_bar = bar_base;                       // 8 x 8 B
   const uint32_t empty_bar = bar_base + 64;                 // 8 x 8 B
   const uint32_t tfull_bar = bar_base + 128;                // 2 x 8 B
   const uint32_t tempty_bar = bar_base + 144;               // 2 x 8 B
   const uint32_t tmem_slot = bar_base + 160;                // 4 B
+  const uint32_t side_bar = bar_base + 176;                 // EPI_BUFS x 8 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -687,6 +738,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
     prefetch_tmap(&p.tma_b);
     prefetch_tmap(&p.tma_d);
     if (p.epi.blend_x != nullptr) prefetch_tmap(&p.tma_d2);
+    if (p.side_mode) prefetch_tmap(&p.tma_side);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -694,6 +746,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
         mbar_init(full_bar + 8 * s, 1);
         mbar_init(empty_bar + 8 * s, 1);
       }
+      for (int i = 0; i < EPI_BUFS; ++i) mbar_init(side_bar + 8 * i, 1);
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar + 8 * a, 1);
         mbar_init(tempty_bar + 8 * a, 2 * NUM_EPI_WARPS);   // the epilogue warps of both CTAs of the pair
@@ -813,6 +866,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
     const EpiParams& e = p.epi;
     const bool fused = (p.splits == 1);
     uint32_t nstore = 0;
+    uint32_t side_issued = 0, side_waited = 0;     // per-warp ring of 2 TMA-staged side boxes
+    const bool side = (p.splits == 1) && p.side_mode != 0;
     int it = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int nt = tile % p.n_tiles;
@@ -837,9 +892,29 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
       float sumsq = 0.0f;
       if (row0 < p.M) {
         const int nchunks = p.bn / 32;
+        if (side && nt * p.bn + cpart * 32 < p.N && cpart < nchunks) {   // side box of this warp's first chunk
+          if (lane == 0) {
+            const uint32_t sl = ew * 2 + (side_issued & 1);
+            mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
+            tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cpart * 32, row0);
+          }
+          ++side_issued;
+        }
         for (int c = cpart; c < nchunks; c += CPARTS) {
           const int n0 = nt * p.bn + c * 32;
           if (n0 >= p.N) break;
+          float sv[32];                              // TMA-staged side operand of this chunk
+          if (side) {
+            const int cn = c + CPARTS;               // prefetch the next chunk's box into the other slot
+            if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
+              if (lane == 0) {
+                const uint32_t sl = ew * 2 + (side_issued & 1);
+                mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
+                tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cn * 32, row0);
+              }
+              ++side_issued;
+            }
+          }
           uint32_t v[32];
           tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 +
                               static_cast<uint32_t>(c * 32), v);
@@ -861,11 +936,30 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
                 v[j] = __float_as_uint(fmaxf(y, e.alpha * y));
               }
             }
+            if (side) {
+              const uint32_t sl = ew * 2 + (side_waited & 1);
+              mbar_wait(side_bar + 8 * sl, (side_waited >> 1) & 1);
+              ++side_waited;
+              const uint32_t sb = side_base + sl * EPI_BOX_BYTES + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint32_t r0, r1, r2, r3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                             : "r"(sb + (static_cast<uint32_t>(j ^ (lane & 7)) << 4))
+                             : "memory");
+                sv[4 * j] = __uint_as_float(r0); sv[4 * j + 1] = __uint_as_float(r1);
+                sv[4 * j + 2] = __uint_as_float(r2); sv[4 * j + 3] = __uint_as_float(r3);
+              }
+              __syncwarp();                          // the slot may be refilled two issues later
+            }
             if (e.aux != nullptr) {
-              if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, t);
+              if (!side) {
+                if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, sv);
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float sl = (row_ok && !(t[j] > 0.0f)) ? e.alpha : 1.0f;
+                const float sl = (row_ok && !(sv[j] > 0.0f)) ? e.alpha : 1.0f;
                 v[j] = __float_as_uint(__uint_as_float(v[j]) * sl);
               }
             }
@@ -902,12 +996,13 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
           }
           ++nstore;
           if (blend) {
-            float t[32];
-            if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, t);
+            if (!side) {
+              if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, sv);
+            }
             const float om = 1.0f - beps;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              v[j] = __float_as_uint(row_ok ? beps * t[j] + om * __uint_as_float(v[j]) : 0.0f);
+              v[j] = __float_as_uint(row_ok ? beps * sv[j] + om * __uint_as_float(v[j]) : 0.0f);
             const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
             if (lane == 0) tma_store_wait_read<1>();
             __syncwarp();
