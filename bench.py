@@ -229,13 +229,13 @@ def dominant_kernel_roofline(tr, batch, torch, pk):
 
     cases = {
         # name: (fn, flops, algorithmic bytes, launches per iteration of this shape class)
-        "critic layer-1 forward [3B x 6605] x [6605 x 200] (TF32 tcgen05, split-K)":
+        "critic layer-1 forward [3B x 6605] x [6605 x 200] (TF32 tcgen05 cta_group::2, split-K 3 + finish)":
             (lambda: gemm(0, 1, X3, W1, H1, 3 * batch, Hd, G, b1, 1), 2.0 * 3 * batch * G * Hd,
              4.0 * (3 * batch * G + G * Hd + 3 * batch * Hd), 5),
-        "critic layer-1 wgrad [6605 x 3B] x [3B x 200] (TF32 tcgen05, split-K)":
+        "critic layer-1 wgrad [6605 x 3B] x [3B x 200] (TF32 tcgen05 cta_group::2, split-K + finish)":
             (lambda: gemm(1, 1, X3, D1, GW1, G, Hd, 3 * batch), 2.0 * 3 * batch * G * Hd,
              4.0 * (3 * batch * G + 3 * batch * Hd + G * Hd), 5),
-        "generator output forward [B x 600] x [600 x 6605] (TF32 tcgen05, bias+LeakyReLU epilogue)":
+        "generator output forward [B x 600] x [600 x 6605] (TF32 tcgen05 cta_group::2, bias+LeakyReLU epilogue)":
             (lambda: gemm(0, 1, GH2, WG3, XT, batch, G, Hg, bg3, 1), 2.0 * batch * G * Hg,
              4.0 * (batch * Hg + Hg * G + batch * G), 6),
     }
@@ -254,8 +254,18 @@ def dominant_kernel_roofline(tr, batch, torch, pk):
     else:
         roof = {"bound": "tensor", "achieved": dom["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": dom["tflops"] / tf32_peak,
-                "peak_note": "TF32 dense = measured bf16 burst / 2 (TF32 not measured separately)"}
-    roof.update({"kernel": dom["kernel"], "ms_per_launch": dom["ms"], "traffic": None, "peak_source": pk["src"],
+                "peak_note": "TF32 dense = measured cuBLAS bf16 burst / 2 (TF32 not in MEASURED_PEAKS.json; "
+                             "the tcgen05 cta_group::2 issue rate measured by scripts/ubench is 1190 TFLOP/s at 1965 MHz)"}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernel + shape from the committed
+    # `ncu --set full` captures (profiles/r01_ncu_full_*.txt); null for shapes that were not captured
+    NCU_TRAFFIC = {"critic layer-1 forward": (335.07e6 + 20.06e6, "profiles/r01_ncu_full_critic_l1_forward.txt"),
+                   "generator output forward": (26.79e6 + 55.53e6, "profiles/r01_ncu_full_generator_output.txt")}
+    traffic, traffic_src = None, None
+    for key, (t, src) in NCU_TRAFFIC.items():
+        if dom["kernel"].startswith(key):
+            traffic, traffic_src = t, src
+    roof.update({"kernel": dom["kernel"], "ms_per_launch": dom["ms"], "traffic": traffic, "traffic_source": traffic_src,
+                 "peak_source": pk["src"],
                  "algorithmic_flops_per_launch": dom["flops"], "algorithmic_bytes_per_launch": dom["bytes"],
                  "others": [{k: r[k] for k in ("kernel", "ms", "tflops", "gbs", "per_iter")} for r in out]})
     return roof
