@@ -481,6 +481,61 @@ class WGANTrainer:
             out.update(r)
         return out if read else None
 
+    def train_iteration_host_indices_graph(self, idxs, zs, epss, z_gen, read: bool = True):
+        """Same contract as train_iteration_host_indices, replayed as ONE CUDA graph: the host->device
+        copies out of the caller's pinned buffers, the gathers, all updates and the device->host copy of the
+        loss scalars are graph nodes.  The graph is keyed by the addresses of the pinned host buffers (refill
+        the same buffers for every iteration, as a feed ring would); new buffers trigger a re-capture."""
+        cfg = self.cfg
+        key = tuple(t.data_ptr() for t in list(idxs) + list(zs) + list(epss) + [z_gen])
+        cache = getattr(self, "_hgraph", None)
+        if cache is None or cache[0] != key:
+            for t in list(idxs) + list(zs) + list(epss) + [z_gen]:
+                assert t.is_pinned(), "graph replay needs pinned host buffers"
+            dev = f"cuda:{self.device}"
+            B = idxs[0].shape[0]
+            n = len(idxs)
+            d_idx = [torch.empty((B,), device=dev, dtype=torch.int64) for _ in range(n)]
+            d_z = [torch.empty((B, cfg.noise_input_size), device=dev) for _ in range(n + 1)]
+            d_eps = [torch.empty((B,), device=dev) for _ in range(n)]
+            h_scal = torch.zeros((8,), dtype=torch.float32).pin_memory()
+
+            def body():
+                for k in range(n):
+                    d_idx[k].copy_(idxs[k], non_blocking=True)
+                    d_z[k].copy_(zs[k], non_blocking=True)
+                    if cfg.lambda_gp != 0:
+                        d_eps[k].copy_(epss[k], non_blocking=True)
+                    x = self.gather(d_idx[k])
+                    self.critic_step(x, d_z[k], d_eps[k] if cfg.lambda_gp != 0 else None, read=False)
+                d_z[n].copy_(z_gen, non_blocking=True)
+                self.generator_step(d_z[n], read=False)
+                h_scal[0:4].copy_(self._grad_arena[NET_CRITIC][-4:], non_blocking=True)
+                h_scal[4:8].copy_(self._grad_arena[NET_GENERATOR][-4:], non_blocking=True)
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()                                   # eager warm-up (this IS a training iteration)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._hgraph = (key, g, h_scal, (d_idx, d_z, d_eps))
+            first = True
+        else:
+            first = False
+        _, g, h_scal, _ = self._hgraph
+        if not first:
+            g.replay()
+        if not read:
+            return None
+        torch.cuda.current_stream().synchronize()
+        s = h_scal.numpy()
+        wass = float(s[0] - s[1])
+        return {"wasserstein": wass, "gp": float(s[2]), "critic_loss": wass + float(s[2]), "gen_loss": -float(s[4])}
+
     def train_iteration_host_indices(self, idxs, zs, epss, z_gen, read: bool = True):
         """One WGAN-GP iteration on the RESIDENT training matrix (set_data) with the per-update host
         inputs of the reference loop [W:188-193] fed from pinned host memory: the minibatch cell

@@ -360,13 +360,14 @@ def run_b200(args):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt.item()), out
 
-        dt_i, out_i = timed(lambda: tr.train_iteration_host_indices(idxs, zs[:nb], es, zs[nb]))
+        dt_i, out_i = timed(lambda: tr.train_iteration_host_indices_graph(idxs, zs[:nb], es, zs[nb]))
         dt_x, out_x = timed(lambda: tr.train_iteration_host(xs, zs[:nb], es, zs[nb]))
         h2d_i = sum(t_.numel() * t_.element_size() for t_ in idxs + zs + es)
         h2d_x = sum(t_.numel() * 4 for t_ in xs + zs + es)
         e2e = {"value": world * args.steps / dt_i, "unit": UNIT, "h2d_bytes_per_step": h2d_i,
                "d2h_bytes_per_step": 32, "ms_per_step": dt_i / args.steps * 1e3,
-               "api": "WGANTrainer.train_iteration_host_indices(idx, z, eps, z_gen): pinned host int64 minibatch "
+               "api": "WGANTrainer.train_iteration_host_indices_graph(idx, z, eps, z_gen) (one CUDA graph incl. the H2D/D2H "
+                      "copies): pinned host int64 minibatch "
                       "indices [W:188] + float32 noise [W:193] + epsilon per critic update, training matrix resident "
                       "in HBM (set_data), device gather; losses read back every iteration",
                "last": out_i,

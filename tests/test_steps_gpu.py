@@ -374,3 +374,36 @@ def test_bulk_sampling_is_chunking_independent():
     got = []
     tr.sample_cells(130, chunk=50, seed=7, sink=lambda r0, cells: got.append((r0, cells.clone())))
     assert [g[0] for g in got] == [0, 50, 100] and torch.equal(torch.cat([g[1] for g in got]), a[:130])
+
+
+def test_host_fed_iterations_agree():
+    """The three host-fed entry points (full x feed, index feed, index feed as one CUDA graph) run the same
+    arithmetic: identical parameters after two iterations on the same host inputs."""
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer
+    B, nb = 32, 2
+    g = torch.Generator().manual_seed(0)
+    data = torch.rand((200, SMALL["gex_size"]), generator=g)
+    idxs = [torch.randint(200, (B,), generator=g).pin_memory() for _ in range(nb)]
+    zs = [torch.rand((B, SMALL["noise_input_size"]), generator=g).pin_memory() for _ in range(nb + 1)]
+    es = [torch.rand((B,), generator=g).pin_memory() for _ in range(nb)]
+    xs = [data[i].contiguous().pin_memory() for i in idxs]
+    outs, scal = [], []
+    for mode in ("x", "idx", "graph"):
+        tr = WGANTrainer(WGANConfig(learn_rate=1e-3, n_critic=nb, **SMALL), max_batch=B, device=0, gemm_mode=1)
+        tr.init_params(seed=2)
+        tr.set_data(data)
+        for _ in range(2):
+            if mode == "x":
+                r = tr.train_iteration_host(xs, zs[:nb], es, zs[nb])
+            elif mode == "idx":
+                r = tr.train_iteration_host_indices(idxs, zs[:nb], es, zs[nb])
+            else:
+                r = tr.train_iteration_host_indices_graph(idxs, zs[:nb], es, zs[nb])
+        torch.cuda.synchronize()
+        outs.append(tr.get_params()); scal.append(r)
+        tr.close()
+    for k in O.PARAM_NAMES:
+        assert np.array_equal(outs[1][k], outs[2][k]), k
+        assert np.allclose(outs[0][k], outs[1][k], rtol=0, atol=1e-6), k
+    for k in scal[1]:
+        assert scal[1][k] == pytest.approx(scal[2][k], rel=1e-6, abs=1e-7)
