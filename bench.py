@@ -410,8 +410,22 @@ def run_b200(args):
                 "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
                 "sampler": sampler, "losses": last}
         print(json.dumps(line), flush=True)
+    # Teardown.  Captured graphs hold NCCL kernels: drop them before the communicator, and never let a
+    # wedged collective teardown keep the job (and the GPUs) alive after the result line is out.
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        import threading
+        threading.Thread(target=lambda: (time.sleep(30), os._exit(0)), daemon=True).start()
+    tr._graph_keepalive = None
+    tr._hgraph = None
+    torch.cuda.synchronize()
+    if world > 1:
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        os._exit(0)
 
 
 def main():
