@@ -148,6 +148,13 @@ def time_cpu(batch, steps, warmup, budget_s):
     """Times `steps` iterations after `warmup`; if that would exceed budget_s, uses a smaller
     batch sample and extrapolates linearly in the batch (stated in `sample`)."""
     import torch
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently make the
+    # CPU arm single-threaded)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncores))
     run = cpu_iteration_runner(batch)
     t0 = time.perf_counter(); run(); t_first = time.perf_counter() - t0
     b = batch
