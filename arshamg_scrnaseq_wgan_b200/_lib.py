@@ -49,6 +49,7 @@ SIGNATURES = {
     "wgan_get_arena": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "wgan_get_scalars": (_I, [_P, _I, _P, _P]),
     "wgan_critic_grads": (_I, [_P, _P, _I, _P, _I, _P, _I, _I, _P]),
+    "wgan_critic_prepare": (_I, [_P, _P, _I, _P, _I, _P, _I, _P]),
     "wgan_critic_apply": (_I, [_P, _P]),
     "wgan_generator_grads": (_I, [_P, _P, _I, _I, _I, _P]),
     "wgan_generator_apply": (_I, [_P, _P]),

@@ -78,6 +78,9 @@ struct wgan_handle {
   int gemm_cluster;                  // preferred cluster size of the tensor-core GEMM (1, 2 or 4)
   int gemm_msub;                     // 0 = auto, 1 / 2 = force 128- / 256-row CTA tiles
   int gemm_2cta;                     // 1 = CTA-pair (cta_group::2) kernel
+  // wgan_critic_prepare ran the parameter-independent-of-the-critic part (input staging, G(z), interpolate)
+  // for exactly these arguments; the next wgan_critic_grads with the same arguments skips it
+  const float* prep_x; const float* prep_z; const float* prep_eps; int prep_rows;
 
   float* P(int t) { return arena[td[t].net][WGAN_KIND_PARAM] + td[t].offset; }
   float* Gr(int t) { return arena[td[t].net][WGAN_KIND_GRAD] + td[t].offset; }
@@ -632,6 +635,7 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->launches = 0;
   h->last_gx_rows = 0;
   h->gemm_cluster = 1;
+  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
   h->gemm_2cta = 1;
   if (const char* env = getenv("WGAN_B200_GEMM_2CTA")) h->gemm_2cta = atoi(env) != 0;
   h->gemm_msub = 0;
@@ -804,6 +808,49 @@ int wgan_get_scalars(wgan_handle* h, int net, float* host4, wgan_stream_t stream
 // ---------------------------------------------------------------------------------------------
 // Critic step gradients  (reference: obj_d [W:137], var_list d_params [W:154])
 // ---------------------------------------------------------------------------------------------
+// Phase A of the critic step: everything that does not depend on the critic's parameters -- input staging,
+// generator forward x~ = G(z) and the interpolate x^.  In data-parallel runs the host issues it for update
+// k+1 while the gradient all-reduce of update k is in flight.
+static int critic_phase_a(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
+                          const float* eps_dev, int rows, cudaStream_t s) {
+  const bool gp = h->cfg.lambda_gp != 0.0f;
+  const int Bl = rows, nh = gp ? 1 : 0;
+  const int G = h->G, Gl = h->Gl;
+  const int real0 = (1 + nh) * Bl;
+  const float* z; int lz;
+  TRY(stage_input(h, z_dev, ldz, Bl, h->Z, h->zbuf, h->Zl, &z, &lz, s));
+  float* xreal_slot = h->xcat + static_cast<size_t>(real0) * Gl;
+  const float* x; int lx;
+  TRY(stage_input(h, x_dev, ldx, Bl, G, xreal_slot, Gl, &x, &lx, s));
+  float* xt = h->xcat;
+  float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;    // interpolates, later overwritten by gx
+  // the interpolate x^ = eps x + (1 - eps) x~ is a second output of the generator-output GEMM
+  static const bool fuse_blend = getenv("WGAN_B200_NO_FUSE_BLEND") == nullptr;
+  if (gp && fuse_blend) {
+    TRY(generator_forward(h, z, lz, Bl, xt, Gl, s, x, lx, eps_dev, xh));
+  } else {
+    TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
+    if (gp) {
+      blend_kernel<<<ew_grid(static_cast<size_t>(Bl) * (Gl / 4), 256, h->num_sms), 256, 0, s>>>(
+          x, lx, xt, Gl, eps_dev, xh, Gl, Bl, Gl / 4);
+      TRY(post_launch(h, "blend_kernel"));
+    }
+  }
+  return 0;
+}
+
+int wgan_critic_prepare(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
+                        const float* eps_dev, int rows, wgan_stream_t stream) {
+  if (!h) return -2;
+  if (!x_dev || !z_dev) FAIL("critic_prepare: null input");
+  TRY(check_rows(h, rows, rows));
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->cfg.lambda_gp != 0.0f && !eps_dev) FAIL("critic_prepare: eps required when lambda_gp != 0");
+  TRY(critic_phase_a(h, x_dev, ldx, z_dev, ldz, eps_dev, rows, static_cast<cudaStream_t>(stream)));
+  h->prep_x = x_dev; h->prep_z = z_dev; h->prep_eps = eps_dev; h->prep_rows = rows;
+  return 0;
+}
+
 int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
                       const float* eps_dev, int rows, int global_batch, wgan_stream_t stream) {
   if (!h) return -2;
@@ -818,30 +865,16 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   const float a = h->cfg.alpha, invB = 1.0f / static_cast<float>(global_batch);
   const int real0 = (1 + nh) * Bl;                       // first real row in the stacked buffers
 
-  // inputs into TMA-legal layouts
-  const float* z; int lz;
-  TRY(stage_input(h, z_dev, ldz, Bl, h->Z, h->zbuf, h->Zl, &z, &lz, s));
+  const bool prepared = (h->prep_x == x_dev && h->prep_z == z_dev && h->prep_eps == eps_dev && h->prep_rows == rows);
+  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
+  if (!prepared) TRY(critic_phase_a(h, x_dev, ldx, z_dev, ldz, eps_dev, rows, s));
+  // where phase A left the inputs
   float* xreal_slot = h->xcat + static_cast<size_t>(real0) * Gl;
-  const float* x; int lx;
-  TRY(stage_input(h, x_dev, ldx, Bl, G, xreal_slot, Gl, &x, &lx, s));
+  const bool x_legal = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && (ldx & 3) == 0;
+  const float* x = x_legal ? x_dev : xreal_slot;
+  const int lx = x_legal ? ldx : Gl;
   const bool x_stacked = (x == xreal_slot && lx == Gl);
-
-  // generator forward (constant in this step)
-  float* xt = h->xcat;
-  float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;    // interpolates, later overwritten by gx
-  // the interpolate x^ = eps x + (1 - eps) x~ is a second output of the generator-output GEMM
-  // (measured: the fused second output makes the epilogue the bottleneck, 125 us vs 61 + 43 us separate)
-  static const bool fuse_blend = getenv("WGAN_B200_NO_FUSE_BLEND") == nullptr;
-  if (gp && fuse_blend) {
-    TRY(generator_forward(h, z, lz, Bl, xt, Gl, s, x, lx, eps_dev, xh));
-  } else {
-    TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
-    if (gp) {
-      blend_kernel<<<ew_grid(static_cast<size_t>(Bl) * (Gl / 4), 256, h->num_sms), 256, 0, s>>>(
-          x, lx, xt, Gl, eps_dev, xh, Gl, Bl, Gl / 4);
-      TRY(post_launch(h, "blend_kernel"));
-    }
-  }
+  float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;
 
   // critic layer 1 on [fake | hat | real]  [W:107-111]
   const EpiParams e1 = epi_bias_lrelu(h->P(T_B1), a);

@@ -222,16 +222,33 @@ class WGANTrainer:
         assert t.stride(1) == 1
         return C.c_void_p(t.data_ptr()), int(t.stride(0)), int(t.shape[0])
 
-    def _allreduce(self, net: int):
+    def _allreduce(self, net: int, overlap=None):
+        """One SUM all-reduce of the flat gradient arena (+ loss scalars) per optimizer step.  `overlap` is
+        host code that enqueues work independent of the reduced gradients (the next update's input pipeline and
+        generator forward); it runs on the compute stream while NCCL reduces on its own stream."""
         if self.world > 1:
-            self.dist.all_reduce(self._grad_arena[net], op=self.dist.ReduceOp.SUM, group=self.group)
+            work = self.dist.all_reduce(self._grad_arena[net], op=self.dist.ReduceOp.SUM, group=self.group,
+                                        async_op=True)
+            if overlap is not None:
+                overlap()
+            work.wait()
+        elif overlap is not None:
+            overlap()
+
+    def critic_prepare(self, x, z, eps=None):
+        """Run the critic-parameter-independent part of the next critic_step(x, z, eps) now."""
+        xp, ldx, rows = self._mat(x, self.cfg.gex_size)
+        zp, ldz, _ = self._mat(z, self.cfg.noise_input_size)
+        ep = C.c_void_p(eps.data_ptr()) if eps is not None else C.c_void_p()
+        self._ck(self.lib.wgan_critic_prepare(self._h, xp, ldx, zp, ldz, ep, rows, _stream()), "critic_prepare")
 
     def scalars(self, net: int) -> np.ndarray:
         out = np.empty(4, np.float32)
         self._ck(self.lib.wgan_get_scalars(self._h, net, out.ctypes.data_as(C.c_void_p), _stream()), "get_scalars")
         return out
 
-    def critic_step(self, x, z, eps=None, apply: bool = True, read: bool = True, global_batch: Optional[int] = None):
+    def critic_step(self, x, z, eps=None, apply: bool = True, read: bool = True, global_batch: Optional[int] = None,
+                    overlap=None):
         """One critic update [W:199]: gradients of obj_d (+GP), all-reduce, Adam.
         x [rows, gex], z [rows, noise], eps [rows] are this rank's shard."""
         xp, ldx, rows = self._mat(x, self.cfg.gex_size)
@@ -242,7 +259,7 @@ class WGANTrainer:
             assert eps.is_cuda and eps.dtype == torch.float32 and eps.numel() == rows and eps.is_contiguous()
         gb = rows * self.world if global_batch is None else int(global_batch)
         self._ck(self.lib.wgan_critic_grads(self._h, xp, ldx, zp, ldz, ep, rows, gb, _stream()), "critic_grads")
-        self._allreduce(NET_CRITIC)
+        self._allreduce(NET_CRITIC, overlap)
         if apply:
             self._ck(self.lib.wgan_critic_apply(self._h, _stream()), "critic_apply")
         if not read:
@@ -369,12 +386,28 @@ class WGANTrainer:
             x = self.gather(self.indices(batch, n, seed, base, counter=counter))
             eps = self.uniform(batch, seed, base, counter=counter) if cfg.lambda_gp != 0 else None
             return self.train_iteration(x, z, eps, read=read)
-        for k in range(cfg.n_critic):
+        def draw(k):
             cid = base + k
             z = self.noise_prior(batch, seed=seed, call_id=cid, counter=counter)
             x = self.gather(self.indices(batch, n, seed, cid, counter=counter))
             eps = self.uniform(batch, seed, cid, counter=counter) if cfg.lambda_gp != 0 else None
-            r = self.critic_step(x, z, eps, read=read)
+            return x, z, eps
+
+        nxt = draw(0)
+        for k in range(cfg.n_critic):
+            x, z, eps = nxt
+            hold = {}
+
+            def ahead(k=k, hold=hold):
+                # while the gradients of update k are being all-reduced: inputs + G(z) + interpolates of k+1
+                if k + 1 < cfg.n_critic:
+                    hold["n"] = draw(k + 1)
+                    self.critic_prepare(*hold["n"])
+
+            r = self.critic_step(x, z, eps, read=read, overlap=ahead if self.world > 1 else None)
+            if self.world == 1:
+                ahead()
+            nxt = hold.get("n")
             if read:
                 out.update(r)
         z = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic, counter=counter)

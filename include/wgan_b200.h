@@ -89,6 +89,11 @@ int wgan_get_scalars(wgan_handle* h, int net, float* host4, wgan_stream_t stream
  * {mean-part D_fake, mean-part D_real, GP}.  */
 int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
                       const float* eps_dev, int rows, int global_batch, wgan_stream_t stream);
+/* Optional: run the part of the critic step that does not depend on the critic's parameters (input
+ * staging, x~ = G(z), interpolates) ahead of time; the next wgan_critic_grads with the SAME x/z/eps/rows
+ * skips it.  Lets a data-parallel host overlap it with the gradient all-reduce of the previous update. */
+int wgan_critic_prepare(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
+                        const float* eps_dev, int rows, wgan_stream_t stream);
 /* Adam update of the critic from its GRAD arena [A:140-151], then beta powers [A:214-225]. */
 int wgan_critic_apply(wgan_handle* h, wgan_stream_t stream);
 /* Generator gradients: d(obj_g)/d(g_params) through the critic [W:138,142,155];
