@@ -127,3 +127,18 @@ def test_gemm_many_tiles_persistent():
     assert r["err"] < TOL[0], r
     r = _run(tr, "dgrad", 4096, 1024, 128, rng, aux=True)
     assert r["err"] < TOL[0], r
+
+
+def test_gemm_random_ragged_shapes():
+    """30 random ragged shapes per layout (tails in M, N and K, tiny and multi-tile sizes, random epilogues)."""
+    tr = _trainer(0)
+    rng = np.random.default_rng(2024)
+    for i in range(30):
+        layout = ("fwd", "dgrad", "wgrad")[i % 3]
+        M = int(rng.integers(1, 700)); N = int(rng.integers(1, 900)); K = int(rng.integers(1, 1500))
+        kw = dict(bias=bool(rng.integers(2)), act=int(rng.integers(2)), aux=bool(rng.integers(2)),
+                  row_scale=bool(rng.integers(2)), sumsq=bool(rng.integers(2)), splits=int(rng.integers(0, 4)))
+        r = _run(tr, layout, M, N, K, rng, **kw)
+        assert r["err"] < 3e-3, (layout, M, N, K, kw, r)
+        if kw["sumsq"]:
+            assert r["sq_err"] < 6e-3, (layout, M, N, K, kw, r)

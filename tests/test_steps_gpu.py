@@ -407,3 +407,27 @@ def test_host_fed_iterations_agree():
         assert np.allclose(outs[0][k], outs[1][k], rtol=0, atol=1e-6), k
     for k in scal[1]:
         assert scal[1][k] == pytest.approx(scal[2][k], rel=1e-6, abs=1e-7)
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("dims,B", [(SMALL, 300), (REF, 130)])
+def test_stacked_real_slot_path_matches_oracle(dims, B, mode):
+    """The resident pipeline gathers the real cells straight into the library's stacked activation buffer, so
+    critic layer 1 and its weight gradient run as single GEMMs over [fake | interpolate | real] rows.  That
+    path must give the same losses and gradients as the oracle (and as the separate-x path)."""
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(dims, B, 10.0, mode)
+    slot = tr.real_slot(B)
+    slot.copy_(xd)
+    s = tr.critic_step(slot, zd, ed, apply=False)
+    so, go = O.critic_step_grads(P, x, z, eps, ocfg)
+    assert abs(s["wasserstein"] - so["wasserstein"]) <= W_TOL[mode] * _dscale(P, x, z), (s, so)
+    assert abs(s["gp"] - so["gp"]) <= gp_tol(mode, B) * abs(so["gp"]), (s, so)
+    _check_grads(tr.get_grads(O.CRITIC_NAMES), go, O.CRITIC_NAMES, mode, B)
+    # prepared variant (data-parallel overlap path): identical result
+    g1 = {k: tr.get_tensor(k, "grad").copy() for k in O.CRITIC_NAMES}
+    slot.copy_(xd)
+    tr.critic_prepare(slot, zd, ed)
+    s2 = tr.critic_step(slot, zd, ed, apply=False)
+    assert s2 == s
+    for k in O.CRITIC_NAMES:
+        assert np.array_equal(g1[k], tr.get_tensor(k, "grad")), k
