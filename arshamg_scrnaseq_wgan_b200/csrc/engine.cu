@@ -15,6 +15,7 @@
 #include <string.h>
 #include <atomic>
 #include <algorithm>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -124,6 +125,29 @@ inline int ew_grid(size_t n, int block, int sms) {
   if (g < 1) g = 1;
   return static_cast<int>(g);
 }
+
+// Every kernel is launched with programmatic stream serialisation (PDL): a dependent grid may be scheduled
+// while its predecessor drains; each kernel executes griddepcontrol.wait before it touches global memory, so
+// ordering is unchanged, only the launch gap (and, for the GEMMs, the barrier/TMEM prologue) overlaps.
+const bool g_pdl = getenv("WGAN_B200_NO_PDL") == nullptr;
+
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface in post_launch
+}
+#define KLAUNCH(kernel, grid, block, smem, stream, ...) \
+  launch_pdl(kernel, dim3(grid), dim3(block), static_cast<size_t>(smem), stream, __VA_ARGS__)
 
 int post_launch(wgan_handle* h, const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -243,13 +267,13 @@ int launch_finish(wgan_handle* h, const float* part, size_t slab, int splits, fl
   if (epi.row_sumsq == nullptr) {
     const size_t n = static_cast<size_t>(M) * ((N + 3) / 4);
     if (splits >= 8 && n <= static_cast<size_t>(h->num_sms) * 32 * 16) {
-      finish_splitk_tall_kernel<<<static_cast<int>((n + 31) / 32), 256, 0, s>>>(part, slab, splits, D, ldd, M, N, epi);
+      KLAUNCH(finish_splitk_tall_kernel, static_cast<int>((n + 31) / 32), 256, 0, s, part, slab, splits, D, ldd, M, N, epi);
       return post_launch(h, "finish_splitk_tall_kernel");
     }
-    finish_splitk_vec4_kernel<<<ew_grid(n, 256, h->num_sms), 256, 0, s>>>(part, slab, splits, D, ldd, M, N, epi);
+    KLAUNCH(finish_splitk_vec4_kernel, ew_grid(n, 256, h->num_sms), 256, 0, s, part, slab, splits, D, ldd, M, N, epi);
     return post_launch(h, "finish_splitk_vec4_kernel");
   }
-  finish_splitk_kernel<<<ew_grid(static_cast<size_t>(M) * 32, 256, h->num_sms), 256, 0, s>>>(part, slab, splits, D,
+  KLAUNCH(finish_splitk_kernel, ew_grid(static_cast<size_t>(M) * 32, 256, h->num_sms), 256, 0, s, part, slab, splits, D,
                                                                                             ldd, M, N, epi);
   return post_launch(h, "finish_splitk_kernel");
 }
@@ -270,13 +294,15 @@ int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int cluster_tile
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   if (max_clusters[dev][p.cluster] == 0) {
     int n = 0;
     cfg.gridDim = dim3(h->num_sms / p.cluster * p.cluster);
@@ -307,13 +333,15 @@ int launch_tc2(wgan_handle* h, const GemmParams& p, size_t smem, int pair_tiles,
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   const int max_pairs = h->num_sms / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
   cfg.gridDim = dim3(pairs * 2);
@@ -341,14 +369,14 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     for (int i = 0; i < nparts; ++i) {
       const Part& pt = parts[i];
       dim3 grid(cdiv(N, 64), cdiv(M, 64));
-      gemm_fp32_kernel<<<grid, 256, 0, s>>>(pt.A, a_mn ? 1 : pt.lda, a_mn ? pt.lda : 1, pt.B,
+      KLAUNCH(gemm_fp32_kernel, grid, 256, 0, s, pt.A, a_mn ? 1 : pt.lda, a_mn ? pt.lda : 1, pt.B,
                                             b_mn ? 1 : pt.ldb, b_mn ? pt.ldb : 1,
                                             raw + slab * i, ldd, M, N, pt.K);
       TRY(post_launch(h, "gemm_fp32_kernel"));
     }
     TRY(launch_finish(h, raw, slab, nparts, D, ldd, M, N, epi, s));
     if (epi.blend_x != nullptr) {
-      blend_kernel<<<ew_grid(static_cast<size_t>(M) * (ldd / 4), 256, h->num_sms), 256, 0, s>>>(
+      KLAUNCH(blend_kernel, ew_grid(static_cast<size_t>(M) * (ldd / 4), 256, h->num_sms), 256, 0, s, 
           epi.blend_x, epi.ld_blend, D, ldd, epi.blend_eps, blend_out, ldd, M, ldd / 4);
       TRY(post_launch(h, "blend_kernel"));
     }
@@ -531,10 +559,10 @@ int colsum_jobs(wgan_handle* h, const ColsumJob* jobs, int njobs, cudaStream_t s
   if (RC < 1) RC = 1;
   a.part_stride = h->colpart_stride;
   dim3 grid(cdiv(maxN, 32), RC, njobs);
-  colsum_partial_kernel<<<grid, 256, 0, s>>>(a, h->colpart);
+  KLAUNCH(colsum_partial_kernel, grid, 256, 0, s, a, h->colpart);
   TRY(post_launch(h, "colsum_partial_kernel"));
   dim3 g2(cdiv(maxN, 256), njobs);
-  colsum_final_kernel<<<g2, 256, 0, s>>>(a, h->colpart, RC);
+  KLAUNCH(colsum_final_kernel, g2, 256, 0, s, a, h->colpart, RC);
   return post_launch(h, "colsum_final_kernel");
 }
 
@@ -550,7 +578,7 @@ int segment_sums(wgan_handle* h, const SumJob* jobs, int njobs, cudaStream_t s) 
   SumJobs a;
   memset(&a, 0, sizeof a);
   for (int j = 0; j < njobs; ++j) a.job[j] = jobs[j];
-  segment_sum_kernel<<<njobs, 1024, 0, s>>>(a);
+  KLAUNCH(segment_sum_kernel, njobs, 1024, 0, s, a);
   return post_launch(h, "segment_sum_kernel");
 }
 
@@ -590,12 +618,12 @@ int check_rows(wgan_handle* h, int rows, int global_batch) {
 
 int adam_apply(wgan_handle* h, int net, cudaStream_t s) {
   const size_t n4 = (h->arena_n[net] - 4) / 4;     // scalar tail excluded
-  adam_kernel<<<ew_grid(n4, 256, h->num_sms), 256, 0, s>>>(
+  KLAUNCH(adam_kernel, ew_grid(n4, 256, h->num_sms), 256, 0, s, 
       h->arena[net][WGAN_KIND_PARAM], h->arena[net][WGAN_KIND_GRAD], h->arena[net][WGAN_KIND_M],
       h->arena[net][WGAN_KIND_V], n4, h->powers[net], h->cfg.learn_rate, h->cfg.beta1, h->cfg.beta2,
       h->cfg.epsilon);
   TRY(post_launch(h, "adam_kernel"));
-  adam_finish_kernel<<<1, 32, 0, s>>>(h->powers[net], h->cfg.beta1, h->cfg.beta2);
+  KLAUNCH(adam_finish_kernel, 1, 32, 0, s, h->powers[net], h->cfg.beta1, h->cfg.beta2);
   return post_launch(h, "adam_finish_kernel");
 }
 
@@ -831,7 +859,7 @@ static int critic_phase_a(wgan_handle* h, const float* x_dev, int ldx, const flo
   } else {
     TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
     if (gp) {
-      blend_kernel<<<ew_grid(static_cast<size_t>(Bl) * (Gl / 4), 256, h->num_sms), 256, 0, s>>>(
+      KLAUNCH(blend_kernel, ew_grid(static_cast<size_t>(Bl) * (Gl / 4), 256, h->num_sms), 256, 0, s, 
           x, lx, xt, Gl, eps_dev, xh, Gl, Bl, Gl / 4);
       TRY(post_launch(h, "blend_kernel"));
     }
@@ -889,7 +917,7 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
   TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, T, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
   // layer 3 + upstream deltas  [W:119-123,137]
-  critic_head_kernel<<<ew_grid(static_cast<size_t>(T) * 32, 256, h->num_sms), 256, 0, s>>>(
+  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(T) * 32, 256, h->num_sms), 256, 0, s, 
       h->h2, Hdl, T, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, invB, gp ? 1.0f : -invB,
       gp ? -invB : 0.0f, a);
   TRY(post_launch(h, "critic_head_kernel"));
@@ -912,7 +940,7 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
     TRY(gemm1(h, false, false, d1_hat, Hdl, W1, ldw1, xh, Gl, Bl, G, Hd, eg, s, &tiles));
     h->last_gx_rows = Bl;
     // norm, penalty, per-row coefficient; g1 <- c . g1
-    gp_coef_kernel<<<ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s>>>(
+    KLAUNCH(gp_coef_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s, 
         h->nsq, tiles, Bl, Bl, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, d1_hat, Hdl, Hd);
     TRY(post_launch(h, "gp_coef_kernel"));
     SumJob pj = {h->pen, sc + WGAN_S_GP, Bl, h->cfg.lambda_gp * invB};
@@ -987,7 +1015,7 @@ int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, 
   const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
   TRY(gemm1(h, false, true, xt, Gl, W1, ldw1, h->h1, Hdl, Bl, Hd, G, epi_bias_lrelu(h->P(T_B1), a), s));
   TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, Bl, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
-  critic_head_kernel<<<ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s>>>(
+  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s, 
       h->h2, Hdl, Bl, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, -invB, 0.f, 0.f, a);
   TRY(post_launch(h, "critic_head_kernel"));
   float* sc = h->scalars(WGAN_NET_GENERATOR);
@@ -1057,7 +1085,7 @@ int wgan_critic_forward(wgan_handle* h, const float* x_dev, int ldx, float* d_ou
             epi_bias_lrelu(h->P(T_B1), a), s));
   TRY(gemm1(h, false, true, h->h1, Hdl, h->P(T_W2), h->td[T_W2].ld, h->h2, Hdl, rows, Hd, Hd,
             epi_bias_lrelu(h->P(T_B2), a), s));
-  critic_head_kernel<<<ew_grid(static_cast<size_t>(rows) * 32, 256, h->num_sms), 256, 0, s>>>(
+  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(rows) * 32, 256, h->num_sms), 256, 0, s, 
       h->h2, Hdl, rows, Hd, h->P(T_W3), h->P(T_B3), d_out_dev, h->d2, rows, 0.f, 0.f, 0.f, a);
   return post_launch(h, "critic_head_kernel");
 }
@@ -1080,17 +1108,17 @@ int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_de
   float* xt = h->xcat;
   float* d3 = h->xcat + static_cast<size_t>(Bl) * Gl;
   TRY(generator_forward(h, z_dev, Z, Bl, xt, Gl, s));
-  latent_residual_kernel<<<Bl, 256, 0, s>>>(xt, Gl, x_dev, ldx, d3, Gl, loss_dev, G, a);
+  KLAUNCH(latent_residual_kernel, Bl, 256, 0, s, xt, Gl, x_dev, ldx, d3, Gl, loss_dev, G, a);
   TRY(post_launch(h, "latent_residual_kernel"));
   const float* Wg3 = h->P(T_WG3); const float* Wg2 = h->P(T_WG2); const float* Wg1 = h->P(T_WG1);
   TRY(gemm1(h, false, false, d3, Gl, Wg3, h->td[T_WG3].ld, h->gd2, Hgl, Bl, Hg, G, epi_mask(h->gh2, Hgl, a), s));
   TRY(gemm1(h, false, false, h->gd2, Hgl, Wg2, h->td[T_WG2].ld, h->gd1, Hgl, Bl, Hg, Hg, epi_mask(h->gh1, Hgl, a), s));
   TRY(gemm1(h, false, false, h->gd1, Hgl, Wg1, h->td[T_WG1].ld, h->dz, Z, Bl, Z, Hg, epi_none(), s));
   const size_t n4 = static_cast<size_t>(Bl) * Z / 4;
-  adam_kernel<<<ew_grid(n4, 256, h->num_sms), 256, 0, s>>>(z_dev, h->dz, m_dev, v_dev, n4, powers_dev, learn_rate,
+  KLAUNCH(adam_kernel, ew_grid(n4, 256, h->num_sms), 256, 0, s, z_dev, h->dz, m_dev, v_dev, n4, powers_dev, learn_rate,
                                                           h->cfg.beta1, h->cfg.beta2, h->cfg.epsilon);
   TRY(post_launch(h, "adam_kernel"));
-  adam_finish_kernel<<<1, 32, 0, s>>>(powers_dev, h->cfg.beta1, h->cfg.beta2);
+  KLAUNCH(adam_finish_kernel, 1, 32, 0, s, powers_dev, h->cfg.beta1, h->cfg.beta2);
   return post_launch(h, "adam_finish_kernel");
 }
 
@@ -1122,7 +1150,7 @@ int wgan_rng_noise_prior(float* out_dev, int ld, int64_t row0, int rows, int dim
   if (upload_poisson_cdf_once() != 0) { g_create_error = "rng_noise_prior: constant upload failed"; return -1; }
   const size_t n = static_cast<size_t>(rows) * dim;
   int grid = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
-  rng_noise_prior_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, ld, row0, rows, dim, sigma,
+  KLAUNCH(rng_noise_prior_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), out_dev, ld, row0, rows, dim, sigma,
                                                                                seed, call_id, 1u, call_id_dev);
   return rng_launch_check("rng_noise_prior_kernel");
 }
@@ -1130,7 +1158,7 @@ int wgan_rng_noise_prior(float* out_dev, int ld, int64_t row0, int rows, int dim
 int wgan_rng_uniform(float* out_dev, int64_t row0, int rows, uint64_t seed, uint32_t call_id,
                      const uint32_t* call_id_dev, wgan_stream_t stream) {
   if (!out_dev || rows <= 0) { g_create_error = "rng_uniform: bad argument"; return -2; }
-  rng_uniform_kernel<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, row0, rows, seed,
+  KLAUNCH(rng_uniform_kernel, cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream), out_dev, row0, rows, seed,
                                                                                      call_id, 2u, call_id_dev);
   return rng_launch_check("rng_uniform_kernel");
 }
@@ -1138,14 +1166,14 @@ int wgan_rng_uniform(float* out_dev, int64_t row0, int rows, uint64_t seed, uint
 int wgan_rng_indices(int64_t* out_dev, int64_t row0, int rows, uint32_t n_cells, uint64_t seed,
                      uint32_t call_id, const uint32_t* call_id_dev, wgan_stream_t stream) {
   if (!out_dev || rows <= 0 || n_cells == 0) { g_create_error = "rng_indices: bad argument"; return -2; }
-  rng_indices_kernel<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, row0, rows, n_cells,
+  KLAUNCH(rng_indices_kernel, cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream), out_dev, row0, rows, n_cells,
                                                                                      seed, call_id, 3u, call_id_dev);
   return rng_launch_check("rng_indices_kernel");
 }
 
 int wgan_counter_add(uint32_t* counter_dev, uint32_t inc, wgan_stream_t stream) {
   if (!counter_dev) { g_create_error = "counter_add: null argument"; return -2; }
-  counter_add_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counter_dev, inc);
+  KLAUNCH(counter_add_kernel, 1, 32, 0, static_cast<cudaStream_t>(stream), counter_dev, inc);
   return rng_launch_check("counter_add_kernel");
 }
 
@@ -1160,7 +1188,7 @@ int wgan_gather_rows(const float* data_dev, int ld_data, const int64_t* idx_dev,
   if (round4(cols) > ld_data || round4(cols) > ld_out) { g_create_error = "gather_rows: ld smaller than padded cols"; return -2; }
   const size_t n = static_cast<size_t>(rows) * cols4;
   int grid = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
-  gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(data_dev, ld_data, idx_dev, out_dev,
+  KLAUNCH(gather_rows_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), data_dev, ld_data, idx_dev, out_dev,
                                                                            ld_out, rows, cols4);
   return rng_launch_check("gather_rows_kernel");
 }

@@ -98,6 +98,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// Programmatic dependent launch: let the next grid be scheduled early / wait for the previous grid's memory.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -315,6 +322,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma_a);
@@ -349,6 +357,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   tcgen05_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_wait();                                  // everything above overlapped the previous kernel's tail
 
   // Persistent schedule over "cluster tiles": the C CTAs of a cluster take C consecutive M tiles of
   // the same N tile and split, and walk the K blocks in lockstep.
@@ -732,6 +741,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma_a);
@@ -765,6 +775,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
   tcgen05_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_wait();                                  // everything above overlapped the previous kernel's tail
 
   // Persistent schedule over "cluster tiles": the C CTAs of a cluster take C consecutive M tiles of
   // the same N tile and split, and walk the K blocks in lockstep.

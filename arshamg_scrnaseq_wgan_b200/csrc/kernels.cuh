@@ -18,6 +18,8 @@ namespace wg {
 // ---------------------------------------------------------------------------------------------
 __global__ void finish_splitk_kernel(const float* __restrict__ part, size_t slab_stride, int splits,
                                      float* out, int ld, int M, int N, EpiParams e) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
@@ -50,6 +52,8 @@ __global__ void finish_splitk_kernel(const float* __restrict__ part, size_t slab
 // small outputs with many splits (K = batch wgrads) still fill the machine.
 __global__ void finish_splitk_vec4_kernel(const float* __restrict__ part, size_t slab_stride, int splits,
                                           float* out, int ld, int M, int N, EpiParams e) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n4 = (N + 3) >> 2;
   const size_t total = static_cast<size_t>(M) * n4;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -88,6 +92,8 @@ __global__ void finish_splitk_vec4_kernel(const float* __restrict__ part, size_t
 __global__ void __launch_bounds__(256)
 finish_splitk_tall_kernel(const float* __restrict__ part, size_t slab_stride, int splits, float* out, int ld,
                           int M, int N, EpiParams e) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n4 = (N + 3) >> 2;
@@ -141,6 +147,8 @@ finish_splitk_tall_kernel(const float* __restrict__ part, size_t slab_stride, in
 __global__ void __launch_bounds__(256)
 gemm_fp32_kernel(const float* __restrict__ A, long sam, long sak, const float* __restrict__ B,
                  long sbn, long sbk, float* __restrict__ C, int ldc, int M, int N, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float As[16][64 + 1];
   __shared__ float Bs[16][64 + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -201,6 +209,8 @@ __global__ void critic_head_kernel(const float* __restrict__ h2, int ld, int row
                                    const float* __restrict__ w3, const float* __restrict__ b3,
                                    float* __restrict__ d, float* __restrict__ dlt, int seg, float c0,
                                    float c1, float c2, float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
     const int s = r / seg;
@@ -230,6 +240,8 @@ struct SumJobs {
   SumJob job[3];
 };
 __global__ void __launch_bounds__(1024) segment_sum_kernel(SumJobs jobs) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const SumJob jb = jobs.job[blockIdx.x];
   float acc = 0.0f;
@@ -254,6 +266,8 @@ __global__ void __launch_bounds__(1024) segment_sum_kernel(SumJobs jobs) {
 __global__ void gp_coef_kernel(const float* __restrict__ nsq, int ntiles, int tile_stride, int rows,
                                float two_lambda_over_B, float* __restrict__ c, float* __restrict__ pen,
                                float* __restrict__ norms, float* __restrict__ g1, int ld, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
     float s = 0.0f;
@@ -274,6 +288,8 @@ __global__ void gp_coef_kernel(const float* __restrict__ nsq, int ntiles, int ti
 __global__ void blend_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ xt,
                              int ldt, const float* __restrict__ eps, float* __restrict__ xh, int ldh,
                              int rows, int cols4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(rows) * cols4;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -313,6 +329,8 @@ struct ColsumArgs {
 };
 
 __global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][33];
   const ColsumJob& jb = a.job[blockIdx.z];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -340,6 +358,8 @@ __global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part) {
 }
 
 __global__ void colsum_final_kernel(ColsumArgs a, const float* __restrict__ part, int RC) {
+  pdl_launch_dependents();
+  pdl_wait();
   const ColsumJob& jb = a.job[blockIdx.y];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= jb.N) return;
@@ -366,6 +386,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n4, const float* __restrict__ pw, float lr,
                             float beta1, float beta2, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float b1p = pw[0], b2p = pw[1];
   const float lr_t = __fdiv_rn(__fmul_rn(lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
   const float omb1 = __fsub_rn(1.0f, beta1), omb2 = __fsub_rn(1.0f, beta2);
@@ -386,6 +408,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 __global__ void adam_finish_kernel(float* pw, float beta1, float beta2) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     pw[0] = __fmul_rn(pw[0], beta1);
     pw[1] = __fmul_rn(pw[1], beta2);
@@ -416,6 +440,8 @@ __constant__ float c_poisson1_cdf[12];
 __global__ void rng_noise_prior_kernel(float* __restrict__ out, int ld, long row0, int rows, int dim,
                                        float sigma, uint64_t seed, uint32_t call_id, uint32_t stream,
                                        const uint32_t* __restrict__ call_id_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (call_id_dev != nullptr) call_id += *call_id_dev;
   const size_t total = static_cast<size_t>(rows) * dim;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -439,6 +465,8 @@ __global__ void rng_noise_prior_kernel(float* __restrict__ out, int ld, long row
 // U[0,1) per global row (epsilon of the interpolates).
 __global__ void rng_uniform_kernel(float* __restrict__ out, long row0, int rows, uint64_t seed,
                                    uint32_t call_id, uint32_t stream, const uint32_t* __restrict__ call_id_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (call_id_dev != nullptr) call_id += *call_id_dev;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
@@ -452,6 +480,8 @@ __global__ void rng_uniform_kernel(float* __restrict__ out, long row0, int rows,
 __global__ void rng_indices_kernel(int64_t* __restrict__ out, long row0, int rows, uint32_t n_cells,
                                    uint64_t seed, uint32_t call_id, uint32_t stream,
                                    const uint32_t* __restrict__ call_id_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (call_id_dev != nullptr) call_id += *call_id_dev;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
@@ -462,12 +492,16 @@ __global__ void rng_indices_kernel(int64_t* __restrict__ out, long row0, int row
 }
 
 __global__ void counter_add_kernel(uint32_t* counter, uint32_t inc) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) *counter += inc;
 }
 
 // Minibatch gather from the resident cells-major matrix: out[r,:] = data[idx[r],:]  [W:188-191]
 __global__ void gather_rows_kernel(const float* __restrict__ data, int ldd, const int64_t* __restrict__ idx,
                                    float* __restrict__ out, int ldo, int rows, int cols4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(rows) * cols4;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -483,6 +517,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ data, int ldd, cons
 __global__ void latent_residual_kernel(const float* __restrict__ xt, int ldt, const float* __restrict__ x,
                                        int ldx, float* __restrict__ d3, int ldd, float* __restrict__ loss,
                                        int cols, float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const int r = blockIdx.x;
   float acc = 0.0f;
