@@ -431,3 +431,42 @@ def test_stacked_real_slot_path_matches_oracle(dims, B, mode):
     assert s2 == s
     for k in O.CRITIC_NAMES:
         assert np.array_equal(g1[k], tr.get_tensor(k, "grad")), k
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_against_committed_golden_fixture(mode):
+    """tests/golden/wgan_small.npz (made by tests/golden/make_golden.py from the fp64 oracle): odd dimensions
+    everywhere (Z 6, Hg 10, G 13, Hd 7, batch 5), so every operand goes through the staging / padding paths."""
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wgan_small.npz"))
+    dims = dict(noise_input_size=6, inflate_to_size=10, gex_size=13, disc_internal_size=7)
+    cfg = WGANConfig(lambda_gp=10.0, learn_rate=1e-3, **dims)
+    tr = WGANTrainer(cfg, max_batch=5, device=0, gemm_mode=mode)
+    P = {k[2:]: gold[k] for k in gold.files if k.startswith("P/")}
+    tr.set_params(P)
+    dev = torch.device("cuda:0")
+    xd, zd, ed = (torch.tensor(gold[k], dtype=torch.float32, device=dev) for k in ("x", "z", "eps"))
+    tol = 5e-3 if mode == 0 else 2e-5             # tiny K: TF32 rounding only, masks are far from zero here
+    s = tr.critic_step(xd, zd, ed, apply=False)
+    g = tr.get_grads(O.CRITIC_NAMES)
+    s2 = tr.generator_step(zd, apply=False)
+    g.update(tr.get_grads(O.GEN_NAMES))
+    got = np.array([s["wasserstein"], s["gp"], s["critic_loss"], s2["gen_loss"]])
+    assert np.allclose(got, gold["scalars"], rtol=tol, atol=tol * 0.1), (got, gold["scalars"])
+    for k in O.PARAM_NAMES:
+        ref = gold["G/" + k]
+        if np.abs(ref).max() == 0:
+            assert np.abs(g[k]).max() == 0
+        else:
+            assert _fro(g[k], ref) < 4 * tol, (k, _fro(g[k], ref))
+    for _ in range(3):
+        tr.critic_step(xd, zd, ed, read=False)
+        tr.generator_step(zd, read=False)
+    for k in O.PARAM_NAMES:
+        ref = gold["P3/" + k]
+        assert _fro(tr.get_tensor(k).reshape(ref.shape), ref) < (2e-3 if mode == 0 else 1e-5), k
+    cells = tr.generator(zd).cpu().numpy()
+    assert _relerr(cells, gold["sample"]) < (5e-3 if mode == 0 else 1e-5)
+    assert np.abs(tr.noise_prior(6, 5, seed=123, call_id=4, row0=10).cpu().numpy() - gold["noise"]).max() < 1e-5
+    assert np.array_equal(tr.uniform(6, 123, 4, row0=10).cpu().numpy(), gold["uniform"])
+    assert np.array_equal(tr.indices(6, 1500, 123, 4, row0=10).cpu().numpy(), gold["indices"])
