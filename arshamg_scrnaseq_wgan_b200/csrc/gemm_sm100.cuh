@@ -1,21 +1,34 @@
-// TF32 tensor-core GEMM for sm_100a: TMA-fed, tcgen05.mma with the accumulator in TMEM,
-// persistent warp-specialised CTAs (1 TMA warp, 1 MMA warp, 4 epilogue warps), fused
-// bias / LeakyReLU / slope-mask / row-scale / row-sum-of-squares epilogue, TMA store.
+// TF32 tensor-core GEMM for sm_100a: TMA-fed, tcgen05.mma with the accumulator in TMEM, persistent
+// warp-specialised CTAs (1 TMA warp, 1 MMA warp, 4 epilogue warps), fused epilogue, TMA store.
+//
+// Two kernels share the structure:
+//   gemm_tf32_2cta_kernel  CTA pairs (tcgen05.mma cta_group::2, cluster (2,1,1)): a pair owns a 256 x bn tile,
+//                          each CTA holds its 128 rows of A, half of the B tile and its rows' accumulator; the
+//                          leader issues the MMAs, every load of the pair completes on the leader's barrier.
+//                          Default: full TF32 issue rate (N/2 cycles per UMMA_K step) and 32 KB stages.
+//   gemm_tf32_kernel       one CTA per 128 x bn tile (cta_group::1, 43 + N/2 cycles per step); used when 256-row
+//                          tiles would pad the row count >10 % more.  Optional B-tile cluster multicast and
+//                          256-row (two-accumulator) tiles are kept as measured-and-rejected experiments.
 //
 // Computes, for every split z of the K range,
 //      D[z][m, n] = epi( sum_{k in split z} A(m, k) * B(n, k) )
-// where A and B are fp32 matrices in global memory read as TF32 by TMA
-// (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), each either "K-major" (K contiguous) or "MN-major"
-// (M resp. N contiguous).  This covers the three dense-layer products of the reference graph
-// with row-major activations [rows, features] and tf.layers.dense kernels [in, out]:
+// where A and B are fp32 matrices in global memory read as TF32 by TMA (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
+// round to nearest), each either "K-major" (K contiguous) or "MN-major" (M resp. N contiguous).  This covers
+// the three dense-layer products of the reference graph with row-major activations [rows, features] and
+// tf.layers.dense kernels [in, out]:
 //      forward   Y  = X  * W      A = X  (K-major),  B = W  (MN-major)   [W:65,71,77,107,113,119]
 //      dgrad     dX = dY * W^T    A = dY (K-major),  B = W  (K-major)    (tf.gradients, [W:154-155])
 //      wgrad     dW = X^T * dY    A = X  (MN-major), B = dY (MN-major)
-// The epilogue (only applied when splits == 1; split-K partials are finished by
-// finish_splitk_kernel in kernels.cu with the same EpiParams) is
+// Shared-memory layouts: K-major tiles are SWIZZLE_128B boxes [rows][32 k]; MN-major 32-bit tiles must be
+// SWIZZLE_128B_BASE32B (TMA 128B_ATOM_32B) and come from a 3-D map (32 floats, K, MN/32) as one box
+// [chunk][32 k][32 mn].  Ragged M / N / K are handled by TMA zero fill and store clipping.
+// The epilogue (applied when splits == 1; split-K partials are finished by finish_splitk_* in kernels.cuh
+// with the same EpiParams) is
 //      y = acc (+ bias[n]);  y = leaky_relu(y);  y *= slope(aux[m,n]);  y *= row_scale[m]
-//      row_sumsq[n_tile][m] = sum_n y^2
-// where slope(h) = h > 0 ? 1 : alpha recovers phi'(a) from the post-activation.
+//      row_sumsq[tile][m] = sum_n y^2;   optional second output  y2 = eps[m] * x[m,n] + (1 - eps[m]) * y
+// where slope(h) = h > 0 ? 1 : alpha recovers phi'(a) from the post-activation.  The [M, N] side
+// operand (aux or x) is staged through shared memory by TMA.  Every kernel starts with
+// griddepcontrol.launch_dependents and waits (griddepcontrol.wait) only after its barrier / TMEM prologue.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
