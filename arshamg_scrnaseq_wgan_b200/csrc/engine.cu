@@ -1003,11 +1003,16 @@ int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, 
   if (!z_dev) FAIL("generator_grads: null input");
   TRY(check_rows(h, rows, global_batch));
   CK(cudaSetDevice(h->cfg.device));
+  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;   // this call reuses the activation workspace
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Bl = rows, Hd = h->Hd, Hdl = h->Hdl, G = h->G, Gl = h->Gl, Hg = h->Hg, Hgl = h->Hgl;
   const float a = h->cfg.alpha, invB = 1.0f / static_cast<float>(global_batch);
-  const float* z; int lz;
-  TRY(stage_input(h, z_dev, ldz, Bl, h->Z, h->zbuf, h->Zl, &z, &lz, s));
+  // z is later the MN-major A operand of the first-layer weight gradient: the last 32-column chunk of an
+  // MN-major tile may read up to 124 B past a row, which the engine's own buffers tolerate (slack) but a
+  // caller's tensor need not -- always work on the staged copy (1.6 MB at batch 4096)
+  CK(cudaMemcpy2DAsync(h->zbuf, static_cast<size_t>(h->Zl) * 4, z_dev, static_cast<size_t>(ldz) * 4,
+                       static_cast<size_t>(h->Z) * 4, Bl, cudaMemcpyDeviceToDevice, s));
+  const float* z = h->zbuf; const int lz = h->Zl;
   float* xt = h->xcat;
   float* d3 = h->xcat + static_cast<size_t>(Bl) * Gl;
   TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
@@ -1056,6 +1061,7 @@ int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int
   if (!z_dev || !out_dev) FAIL("sample: null argument");
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
+  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const float* z; int lz;
   TRY(stage_input(h, z_dev, ldz, rows, h->Z, h->zbuf, h->Zl, &z, &lz, s));
@@ -1076,6 +1082,7 @@ int wgan_critic_forward(wgan_handle* h, const float* x_dev, int ldx, float* d_ou
   if (!x_dev || !d_out_dev) FAIL("critic_forward: null argument");
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
+  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Hd = h->Hd, Hdl = h->Hdl;
   const float a = h->cfg.alpha;
@@ -1102,6 +1109,7 @@ int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_de
   if ((reinterpret_cast<uintptr_t>(z_dev) & 15) != 0) FAIL("latent_fit_step: z must be 16-byte aligned");
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
+  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Bl = rows, G = h->G, Gl = h->Gl, Hg = h->Hg, Hgl = h->Hgl, Z = h->Z;
   const float a = h->cfg.alpha;

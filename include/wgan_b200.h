@@ -11,7 +11,11 @@
  * the caller owns every buffer it passes in; the handle owns parameters, Adam state and
  * workspace; a handle is bound to one GPU and is not thread-safe.
  * All matrices are row-major FP32, one cell (sample) per row, `ld*` = leading dimension
- * in floats.  GEMMs run as TF32 tcgen05 tensor-core kernels (gemm_mode 0) or as FP32
+ * in floats.  An input that is 16-byte aligned with ld % 4 == 0 is consumed in place by TMA (anything
+ * else is staged through a padded copy); the real-cell matrix x of wgan_critic_grads is then also read
+ * as a column-chunked operand whose last 32-column chunk may touch up to 124 bytes past the end of a row,
+ * so an in-place x needs that much readable slack after its last row (any cudaMalloc / framework
+ * allocator block provides it; WGANTrainer.real_slot() avoids the question).  GEMMs run as TF32 tcgen05 tensor-core kernels (gemm_mode 0) or as FP32
  * CUDA-core kernels (gemm_mode 1, verification only).
  */
 #ifndef WGAN_B200_H
