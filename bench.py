@@ -252,7 +252,9 @@ def dominant_kernel_roofline(tr, batch, torch, pk):
         out.append({"kernel": name, "ms": ms, "tflops": flops / ms / 1e9, "gbs": byts / ms / 1e6,
                     "per_iter": per_iter, "flops": flops, "bytes": byts})
     dom = max(out, key=lambda r: r["ms"] * r["per_iter"])
-    tf32_peak = pk["bf16_burst"] / 2.0
+    # TF32 is not in MEASURED_PEAKS.json; measured the same way on this pool (profiles/r01_tf32_peak.txt):
+    # cuBLAS 8192^3 allow_tf32 burst 733.8 TFLOP/s, sustained 595.5 (half the measured bf16 burst would be 804)
+    tf32_peak = 733.8
     t_tensor = dom["flops"] / (tf32_peak * 1e12)
     t_hbm = dom["bytes"] / (pk["hbm_gbs"] * 1e9)
     if t_hbm >= t_tensor:
@@ -261,8 +263,8 @@ def dominant_kernel_roofline(tr, batch, torch, pk):
     else:
         roof = {"bound": "tensor", "achieved": dom["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": dom["tflops"] / tf32_peak,
-                "peak_note": "TF32 dense = measured cuBLAS bf16 burst / 2 (TF32 not in MEASURED_PEAKS.json; "
-                             "the tcgen05 cta_group::2 issue rate measured by scripts/ubench is 1190 TFLOP/s at 1965 MHz)"}
+                "peak_note": "TF32 dense = cuBLAS 8192^3 allow_tf32 burst measured on this pool (profiles/r01_tf32_peak.txt); "
+                             "TF32 is not in MEASURED_PEAKS.json (bf16 burst / 2 would be 804)"}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernel + shape from the committed
     # `ncu --set full` captures (profiles/r01_ncu_full_*.txt); null for shapes that were not captured
     NCU_TRAFFIC = {"critic layer-1 forward": (335.07e6 + 20.06e6, "profiles/r01_ncu_full_critic_l1_forward.txt"),
