@@ -12,7 +12,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libwgan_b200.so")
+LIB_PATH = os.path.join(PKG_DIR, os.environ.get("WGAN_B200_LIB", "libwgan_b200.so"))   # env: A/B builds only
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

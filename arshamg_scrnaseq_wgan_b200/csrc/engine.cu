@@ -250,7 +250,7 @@ int pick_bn_2cta(int N, bool b_mn) {
 
 size_t gemm_smem_bytes(int bn, int msub, int* stages_out, bool side = false) {
   const size_t budget = 232448;                       // 227 KB opt-in maximum per CTA
-  const size_t fixed = 1024 + (side ? 2 : 1) * EPI_BUFS * EPI_BOX_BYTES + 512;
+  const size_t fixed = 1024 + (side ? 2 : 1) * EPI_BUFS * EPI_BOX_BYTES + 512;   // out ring (+ side ring) + barriers
   const size_t stage = static_cast<size_t>(BM) * msub * 128 + static_cast<size_t>(bn) * 128;
   int stages = static_cast<int>((budget - fixed) / stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;

@@ -1,5 +1,5 @@
 // TF32 tensor-core GEMM for sm_100a: TMA-fed, tcgen05.mma with the accumulator in TMEM, persistent
-// warp-specialised CTAs (1 TMA warp, 1 MMA warp, 4 epilogue warps), fused epilogue, TMA store.
+// warp-specialised CTAs (1 TMA warp, 1 MMA warp, 8 epilogue warps), fused epilogue, TMA store.
 //
 // Two kernels share the structure:
 //   gemm_tf32_2cta_kernel  CTA pairs (tcgen05.mma cta_group::2, cluster (2,1,1)): a pair owns a 256 x bn tile,
@@ -39,11 +39,19 @@ namespace wg {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 32;           // 32 tf32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;        // 32 B / sizeof(tf32)
-constexpr int NUM_EPI_WARPS = 4;                    // 4 or 8 (8: two warps per TMEM lane quadrant alternate chunks; measured: no gain)
+// Epilogue shape (A/B-tested on the whole iteration: 4 warps x 2 boxes 361 it/s, 8 x 2 363, 4 x 1 355, 8 x 1 381)
+#ifndef WGAN_EPI_WARPS
+#define WGAN_EPI_WARPS 8
+#endif
+#ifndef WGAN_EPI_NBUF
+#define WGAN_EPI_NBUF 1
+#endif
+constexpr int NUM_EPI_WARPS = WGAN_EPI_WARPS;       // 4 or 8 (8: two warps per TMEM lane quadrant alternate chunks)
+constexpr int EPI_NBUF = WGAN_EPI_NBUF;             // staging boxes per epilogue warp (output ring and side ring)
 constexpr int GEMM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_BOX_BYTES = 32 * 32 * 4;   // one [32 rows][32 cols] fp32 staging box
-constexpr int EPI_BUFS = 2 * NUM_EPI_WARPS;    // two staging boxes per epilogue warp
+constexpr int EPI_BUFS = EPI_NBUF * NUM_EPI_WARPS;
 constexpr int PREFETCH_DIST = 12;             // K blocks between the L2 prefetch and the smem load
 
 struct EpiParams {
@@ -407,7 +415,6 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
               if (!A_MN) {
                 tma_prefetch_2d(&p.tma_a, kp0, m0);
               } else {
-#pragma unroll
                 tma_prefetch_3d(&p.tma_a, 0, kp0, m0 / 32);
               }
             }
@@ -534,7 +541,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
         const int nchunks = p.bn / 32;
         if (side && nt * p.bn + cpart * 32 < p.N && cpart < nchunks) {   // side box of this warp's first chunk
           if (lane == 0) {
-            const uint32_t sl = ew * 2 + (side_issued & 1);
+            const uint32_t sl = ew * EPI_NBUF + (side_issued % EPI_NBUF);
             mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
             tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cpart * 32, row0);
           }
@@ -544,17 +551,6 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           const int n0 = nt * p.bn + c * 32;
           if (n0 >= p.N) break;
           float sv[32];                              // TMA-staged side operand of this chunk
-          if (side) {
-            const int cn = c + CPARTS;               // prefetch the next chunk's box into the other slot
-            if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
-              if (lane == 0) {
-                const uint32_t sl = ew * 2 + (side_issued & 1);
-                mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
-                tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cn * 32, row0);
-              }
-              ++side_issued;
-            }
-          }
           uint32_t v[32];
           tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 +
                               static_cast<uint32_t>(c * 32), v);
@@ -577,8 +573,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
               }
             }
             if (side) {
-              const uint32_t sl = ew * 2 + (side_waited & 1);
-              mbar_wait(side_bar + 8 * sl, (side_waited >> 1) & 1);
+              const uint32_t sl = ew * EPI_NBUF + (side_waited % EPI_NBUF);
+              mbar_wait(side_bar + 8 * sl, (side_waited / EPI_NBUF) & 1);
               ++side_waited;
               const uint32_t sb = side_base + sl * EPI_BOX_BYTES + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
@@ -591,7 +587,16 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
                 sv[4 * j] = __uint_as_float(r0); sv[4 * j + 1] = __uint_as_float(r1);
                 sv[4 * j + 2] = __uint_as_float(r2); sv[4 * j + 3] = __uint_as_float(r3);
               }
-              __syncwarp();                          // the slot may be refilled two issues later
+              __syncwarp();                          // every lane has its values: the ring slot is free again
+              const int cn = c + CPARTS;             // prefetch the next chunk's box while this one is processed
+              if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
+                if (lane == 0) {
+                  const uint32_t sn = ew * EPI_NBUF + (side_issued % EPI_NBUF);
+                  mbar_expect_tx(side_bar + 8 * sn, EPI_BOX_BYTES);
+                  tma_load_2d(side_base + sn * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sn, nt * p.bn + cn * 32, row0);
+                }
+                ++side_issued;
+              }
             }
             if (e.aux != nullptr) {
               if (!side) {
@@ -617,8 +622,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
           } else {
             tmem_ld32_wait(v);
           }
-          const uint32_t buf = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
-          if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago is free again
+          const uint32_t buf = epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (nstore % EPI_NBUF)) * EPI_BOX_BYTES);
+          if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();   // the box used EPI_NBUF stores ago is free again
           __syncwarp();
           const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
@@ -643,8 +648,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               v[j] = __float_as_uint(row_ok ? beps * sv[j] + om * __uint_as_float(v[j]) : 0.0f);
-            const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
-            if (lane == 0) tma_store_wait_read<1>();
+            const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (nstore % EPI_NBUF)) * EPI_BOX_BYTES);
+            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
             __syncwarp();
             const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
@@ -918,7 +923,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
         const int nchunks = p.bn / 32;
         if (side && nt * p.bn + cpart * 32 < p.N && cpart < nchunks) {   // side box of this warp's first chunk
           if (lane == 0) {
-            const uint32_t sl = ew * 2 + (side_issued & 1);
+            const uint32_t sl = ew * EPI_NBUF + (side_issued % EPI_NBUF);
             mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
             tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cpart * 32, row0);
           }
@@ -928,17 +933,6 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
           const int n0 = nt * p.bn + c * 32;
           if (n0 >= p.N) break;
           float sv[32];                              // TMA-staged side operand of this chunk
-          if (side) {
-            const int cn = c + CPARTS;               // prefetch the next chunk's box into the other slot
-            if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
-              if (lane == 0) {
-                const uint32_t sl = ew * 2 + (side_issued & 1);
-                mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
-                tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cn * 32, row0);
-              }
-              ++side_issued;
-            }
-          }
           uint32_t v[32];
           tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 +
                               static_cast<uint32_t>(c * 32), v);
@@ -961,8 +955,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
               }
             }
             if (side) {
-              const uint32_t sl = ew * 2 + (side_waited & 1);
-              mbar_wait(side_bar + 8 * sl, (side_waited >> 1) & 1);
+              const uint32_t sl = ew * EPI_NBUF + (side_waited % EPI_NBUF);
+              mbar_wait(side_bar + 8 * sl, (side_waited / EPI_NBUF) & 1);
               ++side_waited;
               const uint32_t sb = side_base + sl * EPI_BOX_BYTES + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
@@ -975,7 +969,16 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
                 sv[4 * j] = __uint_as_float(r0); sv[4 * j + 1] = __uint_as_float(r1);
                 sv[4 * j + 2] = __uint_as_float(r2); sv[4 * j + 3] = __uint_as_float(r3);
               }
-              __syncwarp();                          // the slot may be refilled two issues later
+              __syncwarp();                          // every lane has its values: the ring slot is free again
+              const int cn = c + CPARTS;             // prefetch the next chunk's box while this one is processed
+              if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
+                if (lane == 0) {
+                  const uint32_t sn = ew * EPI_NBUF + (side_issued % EPI_NBUF);
+                  mbar_expect_tx(side_bar + 8 * sn, EPI_BOX_BYTES);
+                  tma_load_2d(side_base + sn * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sn, nt * p.bn + cn * 32, row0);
+                }
+                ++side_issued;
+              }
             }
             if (e.aux != nullptr) {
               if (!side) {
@@ -1001,8 +1004,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
           } else {
             tmem_ld32_wait(v);
           }
-          const uint32_t buf = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
-          if (lane == 0) tma_store_wait_read<1>();   // the box used two stores ago is free again
+          const uint32_t buf = epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (nstore % EPI_NBUF)) * EPI_BOX_BYTES);
+          if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();   // the box used EPI_NBUF stores ago is free again
           __syncwarp();
           const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
@@ -1027,8 +1030,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               v[j] = __float_as_uint(row_ok ? beps * sv[j] + om * __uint_as_float(v[j]) : 0.0f);
-            const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * 2 + (nstore & 1)) * EPI_BOX_BYTES);
-            if (lane == 0) tma_store_wait_read<1>();
+            const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (nstore % EPI_NBUF)) * EPI_BOX_BYTES);
+            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
             __syncwarp();
             const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
