@@ -267,8 +267,8 @@ def dominant_kernel_roofline(tr, batch, torch, pk):
                              "TF32 is not in MEASURED_PEAKS.json (bf16 burst / 2 would be 804)"}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernel + shape from the committed
     # `ncu --set full` captures (profiles/r01_ncu_full_*.txt); null for shapes that were not captured
-    NCU_TRAFFIC = {"critic layer-1 forward": (335.07e6 + 20.06e6, "profiles/r01_ncu_full_critic_l1_forward.txt"),
-                   "generator output forward": (26.79e6 + 55.53e6, "profiles/r01_ncu_full_generator_output.txt")}
+    NCU_TRAFFIC = {"critic layer-1 forward": (335.06e6 + 20.28e6, "profiles/r01_ncu_full_critic_l1_forward.txt"),
+                   "generator output forward": (26.50e6 + 56.78e6, "profiles/r01_ncu_full_generator_output.txt")}
     traffic, traffic_src = None, None
     for key, (t, src) in NCU_TRAFFIC.items():
         if dom["kernel"].startswith(key):
