@@ -428,7 +428,8 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
       // with at least 8 K blocks per split; otherwise the best-filling one
       const int slots = h->num_sms / ctas_per_tile;
       const int units = tiles * nparts;
-      const int max_sp = std::max(1, std::min(total_kb / 8, 64));
+      // short reductions (K < 1024) are not split: the finish pass would cost more than the idle SMs
+      const int max_sp = total_kb < 32 ? 1 : std::max(1, std::min(total_kb / 8, 64));
       double best_eff = 0.0;
       for (int c = 1; c <= max_sp; ++c) {
         const double eff = static_cast<double>(units) * c / (static_cast<double>(cdiv(units * c, slots)) * slots);
@@ -622,9 +623,7 @@ int adam_apply(wgan_handle* h, int net, cudaStream_t s) {
       h->arena[net][WGAN_KIND_PARAM], h->arena[net][WGAN_KIND_GRAD], h->arena[net][WGAN_KIND_M],
       h->arena[net][WGAN_KIND_V], n4, h->powers[net], h->cfg.learn_rate, h->cfg.beta1, h->cfg.beta2,
       h->cfg.epsilon);
-  TRY(post_launch(h, "adam_kernel"));
-  KLAUNCH(adam_finish_kernel, 1, 32, 0, s, h->powers[net], h->cfg.beta1, h->cfg.beta2);
-  return post_launch(h, "adam_finish_kernel");
+  return post_launch(h, "adam_kernel");
 }
 
 }  // namespace
@@ -922,10 +921,6 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
       gp ? -invB : 0.0f, a);
   TRY(post_launch(h, "critic_head_kernel"));
   float* sc = h->scalars(WGAN_NET_CRITIC);
-  {
-    SumJob jobs[2] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + real0, sc + WGAN_S_DREAL, Bl, invB}};
-    TRY(segment_sums(h, jobs, 2, s));
-  }
   // delta1 / g1 = (delta2 W2^T) . slope(h1)
   TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, T, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
 
@@ -943,14 +938,17 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
     KLAUNCH(gp_coef_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s, 
         h->nsq, tiles, Bl, Bl, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, d1_hat, Hdl, Hd);
     TRY(post_launch(h, "gp_coef_kernel"));
-    SumJob pj = {h->pen, sc + WGAN_S_GP, Bl, h->cfg.lambda_gp * invB};
-    TRY(segment_sums(h, &pj, 1, s));
+    SumJob jobs[3] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + real0, sc + WGAN_S_DREAL, Bl, invB},
+                      {h->pen, sc + WGAN_S_GP, Bl, h->cfg.lambda_gp * invB}};
+    TRY(segment_sums(h, jobs, 3, s));                    // loss scalars: mean parts of D_fake / D_real, penalty
     // parameter-gradient-of-norm pass: v1 = c . (gx W1) . s1 (in place over h1_hat), v2 = (v1 W2) . s2
     EpiParams ev1 = epi_mask(h1_hat, Hdl, a);
     ev1.row_scale = h->crow;
     TRY(gemm1(h, false, true, xh, Gl, W1, ldw1, h1_hat, Hdl, Bl, Hd, G, ev1, s));
     TRY(gemm1(h, false, true, h1_hat, Hdl, W2, ldw2, h->v2, Hdl, Bl, Hd, Hd, epi_mask(h2_hat, Hdl, a), s));
   } else {
+    SumJob jobs[2] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + real0, sc + WGAN_S_DREAL, Bl, invB}};
+    TRY(segment_sums(h, jobs, 2, s));
     CK(cudaMemsetAsync(sc + WGAN_S_GP, 0, 4, s));
   }
 
@@ -1125,9 +1123,7 @@ int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_de
   const size_t n4 = static_cast<size_t>(Bl) * Z / 4;
   KLAUNCH(adam_kernel, ew_grid(n4, 256, h->num_sms), 256, 0, s, z_dev, h->dz, m_dev, v_dev, n4, powers_dev, learn_rate,
                                                           h->cfg.beta1, h->cfg.beta2, h->cfg.epsilon);
-  TRY(post_launch(h, "adam_kernel"));
-  KLAUNCH(adam_finish_kernel, 1, 32, 0, s, powers_dev, h->cfg.beta1, h->cfg.beta2);
-  return post_launch(h, "adam_finish_kernel");
+  return post_launch(h, "adam_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------

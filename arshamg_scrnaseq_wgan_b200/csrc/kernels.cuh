@@ -373,8 +373,8 @@ __global__ void colsum_final_kernel(ColsumArgs a, const float* __restrict__ part
 //   lr_t = lr * sqrt(1 - b2p) / (1 - b1p);  m += (g - m)(1 - b1);  v += (g*g - v)(1 - b2)
 //   var -= (m * lr_t) / (sqrt(v) + eps)            (epsilon OUTSIDE the bias correction)
 // Explicit _rn intrinsics: no FMA contraction, so the update is bit-identical to the FP32 oracle.
-// The beta powers live on the device (pw[0] = b1p, pw[1] = b2p) and are advanced by
-// adam_finish_kernel once all tensors are updated [A:214-225].
+// The beta powers live on the device (pw[0] = b1p, pw[1] = b2p, pw[2] = block counter) and are advanced by the
+// last block of the launch, once every block has read them and all tensors are updated [A:214-225].
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr_t,
                                          float omb1, float omb2, float eps) {
@@ -384,7 +384,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, size_t n4, const float* __restrict__ pw, float lr,
+                            float* __restrict__ v, size_t n4, float* __restrict__ pw, float lr,
                             float beta1, float beta2, float eps) {
   pdl_launch_dependents();
   pdl_wait();
@@ -405,14 +405,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
   }
-}
-
-__global__ void adam_finish_kernel(float* pw, float beta1, float beta2) {
-  pdl_launch_dependents();
-  pdl_wait();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    pw[0] = __fmul_rn(pw[0], beta1);
-    pw[1] = __fmul_rn(pw[1], beta2);
+  // _finish [A:214-225]: the beta powers advance once, after every block has read them.  pw[2] is a
+  // block counter (bit pattern of an unsigned int); the last block to arrive updates the powers and rearms it.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int* counter = reinterpret_cast<unsigned int*>(pw + 2);
+    const unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      pw[0] = __fmul_rn(b1p, beta1);
+      pw[1] = __fmul_rn(b2p, beta2);
+      *counter = 0u;
+      __threadfence();
+    }
   }
 }
 
