@@ -533,16 +533,30 @@ class WGANTrainer:
             d_eps = [torch.empty((B,), device=dev) for _ in range(n)]
             h_scal = torch.zeros((8,), dtype=torch.float32).pin_memory()
 
+            copy_stream = torch.cuda.Stream(device=dev)
+            ready = [torch.cuda.Event() for _ in range(n + 1)]
+
             def body():
+                # all host->device copies of the iteration go to a second stream (a fork inside the graph), so
+                # the feed of update k+1 overlaps the kernels of update k
+                main = torch.cuda.current_stream()
+                copy_stream.wait_stream(main)
+                with torch.cuda.stream(copy_stream):
+                    for k in range(n):
+                        d_idx[k].copy_(idxs[k], non_blocking=True)
+                        d_z[k].copy_(zs[k], non_blocking=True)
+                        if cfg.lambda_gp != 0:
+                            d_eps[k].copy_(epss[k], non_blocking=True)
+                        ready[k].record(copy_stream)
+                    d_z[n].copy_(z_gen, non_blocking=True)
+                    ready[n].record(copy_stream)
                 for k in range(n):
-                    d_idx[k].copy_(idxs[k], non_blocking=True)
-                    d_z[k].copy_(zs[k], non_blocking=True)
-                    if cfg.lambda_gp != 0:
-                        d_eps[k].copy_(epss[k], non_blocking=True)
+                    main.wait_event(ready[k])
                     x = self.gather(d_idx[k])
                     self.critic_step(x, d_z[k], d_eps[k] if cfg.lambda_gp != 0 else None, read=False)
-                d_z[n].copy_(z_gen, non_blocking=True)
+                main.wait_event(ready[n])
                 self.generator_step(d_z[n], read=False)
+                main.wait_stream(copy_stream)
                 h_scal[0:4].copy_(self._grad_arena[NET_CRITIC][-4:], non_blocking=True)
                 h_scal[4:8].copy_(self._grad_arena[NET_GENERATOR][-4:], non_blocking=True)
 
