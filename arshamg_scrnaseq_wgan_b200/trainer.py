@@ -446,6 +446,44 @@ class WGANTrainer:
         _ = per_it
         return graph.replay
 
+    # ------------------------------------------------------------------ training driver [W:166-208]
+    def train(self, n_train_steps: Optional[int] = None, batch_size: Optional[int] = None, seed: int = 0,
+              logger=None, log_every: int = 100, checkpoint_path: Optional[str] = None, save_every: int = 1000,
+              use_graph: bool = True, start_step: int = 0):
+        """The reference's training loop [W:182-203] on the resident matrix (set_data): n_train_steps
+        iterations (default cfg.n_train_steps = 10000 [W:9]) at cfg.batch_size [W:11]; a state dump every
+        `save_every` = 1000 iterations and once at the end [W:201-205]; scalar summaries loss/gen, loss/disc
+        (the reference writes them every iteration [W:196-197]; here every `log_every` to avoid a host sync per
+        iteration).  Iterations are CUDA-graph replays.  Returns the last logged losses."""
+        from .checkpoint import save_checkpoint
+        cfg = self.cfg
+        n = cfg.n_train_steps if n_train_steps is None else int(n_train_steps)
+        B = cfg.batch_size if batch_size is None else int(batch_size)
+        assert self._data is not None, "call set_data(cells_by_genes) first"
+        last = {}
+        replay = None
+        for i in range(start_step, start_step + n):
+            want_log = (logger is not None or i == start_step + n - 1) and ((i + 1) % log_every == 0 or i == start_step + n - 1)
+            if want_log or not use_graph:
+                last = self.train_iteration_resident(i, B, seed=seed, read=want_log) or last
+                replay = None                       # the eager iteration advanced past the graph's counter
+                if want_log and logger is not None:
+                    logger.log(i, last)
+            else:
+                if replay is None:
+                    replay = self.capture_iteration(B, seed=seed, start_it=i)   # runs iteration i eagerly
+                else:
+                    replay()
+            if checkpoint_path is not None and (i % save_every == 0 or i == start_step + n - 1):
+                save_checkpoint(self, checkpoint_path, global_step=i + 1)
+        return last
+
+    def generate(self, num_cells: Optional[int] = None, seed: int = 0) -> torch.Tensor:
+        """[W:217-221]: num_cells_generate (+1) cells from fresh noise -- one batched pass instead of 501
+        single-cell session runs."""
+        n = (self.cfg.num_cells_generate + 1) if num_cells is None else int(num_cells)
+        return self.sample_cells(n, seed=seed)
+
     # ------------------------------------------------------------------ bulk sampling (BASELINE config 5)
     def sample_cells(self, n_cells: int, chunk: Optional[int] = None, seed: int = 0, sink=None,
                      first_row: Optional[int] = None) -> Optional[torch.Tensor]:

@@ -470,3 +470,26 @@ def test_against_committed_golden_fixture(mode):
     assert np.abs(tr.noise_prior(6, 5, seed=123, call_id=4, row0=10).cpu().numpy() - gold["noise"]).max() < 1e-5
     assert np.array_equal(tr.uniform(6, 123, 4, row0=10).cpu().numpy(), gold["uniform"])
     assert np.array_equal(tr.indices(6, 1500, 123, 4, row0=10).cpu().numpy(), gold["indices"])
+
+
+def test_training_driver_matches_eager_loop(tmp_path):
+    """WGANTrainer.train (graph replays + periodic eager logging / state dumps, [W:182-205]) follows exactly
+    the same trajectory as calling train_iteration_resident for every iteration."""
+    from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer
+    from arshamg_scrnaseq_wgan_b200.checkpoint import ScalarLogger
+    data = torch.rand((200, SMALL["gex_size"]), device="cuda:0")
+    cfg = WGANConfig.reference_literal(learn_rate=1e-3, batch_size=16, **SMALL)
+    a = WGANTrainer(cfg, max_batch=64, device=0); a.init_params(1); a.set_data(data)
+    b = WGANTrainer(cfg, max_batch=64, device=0); b.init_params(1); b.set_data(data)
+    log = ScalarLogger(str(tmp_path / "tb"))
+    last = a.train(n_train_steps=23, seed=4, logger=log, log_every=10, checkpoint_path=str(tmp_path / "ck.npz"), save_every=10)
+    log.close()
+    for it in range(23):
+        r = b.train_iteration_resident(it, 16, seed=4, read=(it == 22))
+    torch.cuda.synchronize()
+    assert last == r
+    for k in O.PARAM_NAMES:
+        assert np.array_equal(a.get_tensor(k), b.get_tensor(k)), k
+    assert int(np.load(tmp_path / "ck.npz")["global_step"]) == 23
+    cells = a.generate()
+    assert cells.shape == (501, SMALL["gex_size"])
