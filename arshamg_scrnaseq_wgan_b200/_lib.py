@@ -52,6 +52,7 @@ SIGNATURES = {
     "wgan_critic_prepare": (_I, [_P, _P, _I, _P, _I, _P, _I, _P]),
     "wgan_critic_apply": (_I, [_P, _P]),
     "wgan_generator_grads": (_I, [_P, _P, _I, _I, _I, _P]),
+    "wgan_generator_prepare": (_I, [_P, _P, _I, _I, _P]),
     "wgan_generator_apply": (_I, [_P, _P]),
     "wgan_sample": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "wgan_critic_forward": (_I, [_P, _P, _I, _P, _I, _P]),

@@ -82,6 +82,7 @@ struct wgan_handle {
   // wgan_critic_prepare ran the parameter-independent-of-the-critic part (input staging, G(z), interpolate)
   // for exactly these arguments; the next wgan_critic_grads with the same arguments skips it
   const float* prep_x; const float* prep_z; const float* prep_eps; int prep_rows;
+  const float* gprep_z; int gprep_rows;   // same for wgan_generator_prepare / wgan_generator_grads
 
   float* P(int t) { return arena[td[t].net][WGAN_KIND_PARAM] + td[t].offset; }
   float* Gr(int t) { return arena[td[t].net][WGAN_KIND_GRAD] + td[t].offset; }
@@ -663,6 +664,7 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->last_gx_rows = 0;
   h->gemm_cluster = 1;
   h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
+  h->gprep_z = nullptr; h->gprep_rows = 0;
   h->gemm_2cta = 1;
   if (const char* env = getenv("WGAN_B200_GEMM_2CTA")) h->gemm_2cta = atoi(env) != 0;
   h->gemm_msub = 0;
@@ -840,6 +842,7 @@ int wgan_get_scalars(wgan_handle* h, int net, float* host4, wgan_stream_t stream
 // k+1 while the gradient all-reduce of update k is in flight.
 static int critic_phase_a(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
                           const float* eps_dev, int rows, cudaStream_t s) {
+  h->gprep_z = nullptr; h->gprep_rows = 0;               // shares zbuf / gh1 / gh2 / xcat with the generator step
   const bool gp = h->cfg.lambda_gp != 0.0f;
   const int Bl = rows, nh = gp ? 1 : 0;
   const int G = h->G, Gl = h->Gl;
@@ -995,6 +998,27 @@ int wgan_critic_apply(wgan_handle* h, wgan_stream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // Generator step gradients  (obj_g = -mean(D(G(z))) [W:138], var_list g_params [W:155])
 // ---------------------------------------------------------------------------------------------
+// Phase A of the generator step: stage z and run the generator forward (does not depend on the critic).
+static int generator_phase_a(wgan_handle* h, const float* z_dev, int ldz, int rows, cudaStream_t s) {
+  // z is later the MN-major A operand of the first-layer weight gradient: the last 32-column chunk of an
+  // MN-major tile may read up to 124 B past a row, which the engine's own buffers tolerate (slack) but a
+  // caller's tensor need not -- always work on the staged copy (1.6 MB at batch 4096)
+  CK(cudaMemcpy2DAsync(h->zbuf, static_cast<size_t>(h->Zl) * 4, z_dev, static_cast<size_t>(ldz) * 4,
+                       static_cast<size_t>(h->Z) * 4, rows, cudaMemcpyDeviceToDevice, s));
+  return generator_forward(h, h->zbuf, h->Zl, rows, h->xcat, h->Gl, s);
+}
+
+int wgan_generator_prepare(wgan_handle* h, const float* z_dev, int ldz, int rows, wgan_stream_t stream) {
+  if (!h) return -2;
+  if (!z_dev) FAIL("generator_prepare: null input");
+  TRY(check_rows(h, rows, rows));
+  CK(cudaSetDevice(h->cfg.device));
+  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
+  TRY(generator_phase_a(h, z_dev, ldz, rows, static_cast<cudaStream_t>(stream)));
+  h->gprep_z = z_dev; h->gprep_rows = rows;
+  return 0;
+}
+
 int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, int global_batch,
                          wgan_stream_t stream) {
   if (!h) return -2;
@@ -1005,15 +1029,12 @@ int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Bl = rows, Hd = h->Hd, Hdl = h->Hdl, G = h->G, Gl = h->Gl, Hg = h->Hg, Hgl = h->Hgl;
   const float a = h->cfg.alpha, invB = 1.0f / static_cast<float>(global_batch);
-  // z is later the MN-major A operand of the first-layer weight gradient: the last 32-column chunk of an
-  // MN-major tile may read up to 124 B past a row, which the engine's own buffers tolerate (slack) but a
-  // caller's tensor need not -- always work on the staged copy (1.6 MB at batch 4096)
-  CK(cudaMemcpy2DAsync(h->zbuf, static_cast<size_t>(h->Zl) * 4, z_dev, static_cast<size_t>(ldz) * 4,
-                       static_cast<size_t>(h->Z) * 4, Bl, cudaMemcpyDeviceToDevice, s));
+  const bool prepared = (h->gprep_z == z_dev && h->gprep_rows == rows);
+  h->gprep_z = nullptr; h->gprep_rows = 0;
+  if (!prepared) TRY(generator_phase_a(h, z_dev, ldz, rows, s));
   const float* z = h->zbuf; const int lz = h->Zl;
   float* xt = h->xcat;
   float* d3 = h->xcat + static_cast<size_t>(Bl) * Gl;
-  TRY(generator_forward(h, z, lz, Bl, xt, Gl, s));
   const float* W1 = h->P(T_W1); const int ldw1 = h->td[T_W1].ld;
   const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
   TRY(gemm1(h, false, true, xt, Gl, W1, ldw1, h->h1, Hdl, Bl, Hd, G, epi_bias_lrelu(h->P(T_B1), a), s));

@@ -247,6 +247,11 @@ class WGANTrainer:
         self._ck(self.lib.wgan_get_scalars(self._h, net, out.ctypes.data_as(C.c_void_p), _stream()), "get_scalars")
         return out
 
+    def generator_prepare(self, z):
+        """Run the critic-independent part (z staging, G(z)) of the next generator_step(z) now."""
+        zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
+        self._ck(self.lib.wgan_generator_prepare(self._h, zp, ldz, rows, _stream()), "generator_prepare")
+
     def critic_step(self, x, z, eps=None, apply: bool = True, read: bool = True, global_batch: Optional[int] = None,
                     overlap=None):
         """One critic update [W:199]: gradients of obj_d (+GP), all-reduce, Adam.
@@ -399,19 +404,23 @@ class WGANTrainer:
             hold = {}
 
             def ahead(k=k, hold=hold):
-                # while the gradients of update k are being all-reduced: inputs + G(z) + interpolates of k+1
+                # while the gradients of update k are being all-reduced: inputs + G(z) + interpolates of k+1,
+                # or, after the last critic update, the noise + G(z) of the generator update
                 if k + 1 < cfg.n_critic:
                     hold["n"] = draw(k + 1)
                     self.critic_prepare(*hold["n"])
+                else:
+                    hold["zg"] = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic, counter=counter)
+                    self.generator_prepare(hold["zg"])
 
             r = self.critic_step(x, z, eps, read=read, overlap=ahead if self.world > 1 else None)
             if self.world == 1:
                 ahead()
             nxt = hold.get("n")
+            zg = hold.get("zg")
             if read:
                 out.update(r)
-        z = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic, counter=counter)
-        r = self.generator_step(z, read=read)
+        r = self.generator_step(zg, read=read)
         if read:
             out.update(r)
         return out if read else None

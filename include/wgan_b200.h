@@ -104,6 +104,9 @@ int wgan_critic_apply(wgan_handle* h, wgan_stream_t stream);
  * scalar WGAN_S_DFAKE = mean-part of D(G(z)) (obj_g = -that). */
 int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, int global_batch,
                          wgan_stream_t stream);
+/* Optional: stage z and run x~ = G(z) ahead of wgan_generator_grads(same z, rows) (overlap with the last
+ * critic all-reduce in data-parallel runs). */
+int wgan_generator_prepare(wgan_handle* h, const float* z_dev, int ldz, int rows, wgan_stream_t stream);
 int wgan_generator_apply(wgan_handle* h, wgan_stream_t stream);
 
 /* ---- sampling: G(z) for a batch of cells (replaces the batch-1 loop [W:217-221]) ---- */
