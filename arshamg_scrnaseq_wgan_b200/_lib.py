@@ -23,7 +23,7 @@ class WganConfig(C.Structure):
     _fields_ = [
         ("noise_input_size", C.c_int32), ("inflate_to_size", C.c_int32), ("gex_size", C.c_int32),
         ("disc_internal_size", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32),
-        ("gemm_mode", C.c_int32), ("reserved0", C.c_int32),
+        ("gemm_mode", C.c_int32), ("gp_form", C.c_int32),
         ("learn_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
         ("alpha", C.c_float), ("lambda_gp", C.c_float), ("reserved1", C.c_float), ("reserved2", C.c_float),
     ]

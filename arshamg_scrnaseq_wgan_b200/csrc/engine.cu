@@ -72,6 +72,7 @@ struct wgan_handle {
   // workspace
   float *zbuf, *gh1, *gh2, *xcat, *h1, *h2, *d2, *d1, *dout, *v2, *gd2, *gd1, *dz;
   float *nsq, *crow, *pen, *norms, *colpart, *splitws, *sample_tmp;
+  float *gram_k, *gram_s, *gram_t;   // Gram form of the penalty: W1^T W1, (c g1)^T g1 [Hd, Hd]; g1 K [R, Hd]
   int colpart_stride;
   size_t splitws_n;
   int nsq_tiles_max;
@@ -353,7 +354,11 @@ int launch_tc2(wgan_handle* h, const GemmParams& p, size_t smem, int pair_tiles,
 // D[M,N] = epi( sum_parts A_i * B_i ).  a_mn/b_mn: operand majors (see gemm_sm100.cuh).
 int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts, float* D, int ldd,
              int M, int N, const EpiParams& epi, int* sumsq_tiles, int force_splits, cudaStream_t s,
-             float* blend_out = nullptr) {
+             float* blend_out = nullptr, int ws_slab0 = 0, int* raw_slabs = nullptr, bool raw_force_ws = false) {
+  // raw_slabs != nullptr: leave the raw products for the caller's own finish pass (no epilogue, no finish
+  // kernel).  They go to slabs [ws_slab0, ws_slab0 + *raw_slabs) of the split workspace, or -- single
+  // unsplit product and !raw_force_ws -- straight into D (*raw_slabs = 0).
+  const bool raw = raw_slabs != nullptr;
   if (M <= 0 || N <= 0) FAIL("gemm: empty output %dx%d", M, N);
   if (epi.blend_x != nullptr) force_splits = 1;       // the second output only exists in the fused epilogue
   for (int i = 0; i < nparts; ++i)
@@ -364,18 +369,20 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     // FP32 CUDA-core verification path: raw products into slabs, then the shared finish kernel.
     // raw products go through the workspace so that an epilogue operand aliasing D (in-place
     // slope mask) is still intact when the finish kernel reads it
-    const bool ws_fits = slab * nparts <= h->splitws_n;
-    if (!ws_fits && (nparts > 1 || epi.aux == D)) FAIL("gemm: split workspace too small");
-    float* raw = ws_fits ? h->splitws : D;
+    const bool raw_direct = raw && nparts == 1 && !raw_force_ws;
+    const bool ws_fits = !raw_direct && slab * (ws_slab0 + nparts) <= h->splitws_n;
+    if (!ws_fits && !raw_direct && (nparts > 1 || epi.aux == D || raw)) FAIL("gemm: split workspace too small");
+    float* raw_out = ws_fits ? h->splitws + slab * ws_slab0 : D;
     for (int i = 0; i < nparts; ++i) {
       const Part& pt = parts[i];
       dim3 grid(cdiv(N, 64), cdiv(M, 64));
       KLAUNCH(gemm_fp32_kernel, grid, 256, 0, s, pt.A, a_mn ? 1 : pt.lda, a_mn ? pt.lda : 1, pt.B,
                                             b_mn ? 1 : pt.ldb, b_mn ? pt.ldb : 1,
-                                            raw + slab * i, ldd, M, N, pt.K);
+                                            raw_out + slab * i, ldd, M, N, pt.K);
       TRY(post_launch(h, "gemm_fp32_kernel"));
     }
-    TRY(launch_finish(h, raw, slab, nparts, D, ldd, M, N, epi, s));
+    if (raw) { *raw_slabs = raw_direct ? 0 : nparts; return 0; }
+    TRY(launch_finish(h, raw_out, slab, nparts, D, ldd, M, N, epi, s));
     if (epi.blend_x != nullptr) {
       KLAUNCH(blend_kernel, ew_grid(static_cast<size_t>(M) * (ldd / 4), 256, h->num_sms), 256, 0, s, 
           epi.blend_x, epi.ld_blend, D, ldd, epi.blend_eps, blend_out, ldd, M, ldd / 4);
@@ -446,14 +453,16 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     kbps[i] = per;
     total_splits += sp;
   }
-  if (total_splits > 1 && slab * total_splits > h->splitws_n) {
+  if (total_splits > 1 && slab * (ws_slab0 + total_splits) > h->splitws_n) {
     if (nparts > 1) FAIL("gemm: split workspace too small for %d slabs of %zu floats", total_splits, slab);
     splits[0] = 1;
     kbps[0] = cdiv(parts[0].K, BK);
     total_splits = 1;
   }
-  const bool direct = (total_splits == 1);
-  float* out = direct ? D : h->splitws;
+  const bool to_ws = total_splits > 1 || (raw && raw_force_ws);
+  if (to_ws && slab * (ws_slab0 + total_splits) > h->splitws_n) FAIL("gemm: split workspace too small");
+  const bool direct = !to_ws;
+  float* out = direct ? D : h->splitws + slab * ws_slab0;
   if (!direct && side) {                               // split partials skip the fused epilogue: no side ring
     side = false;
     smem = two_cta ? gemm_smem_bytes(bn / 2, 1, &stages, false) : gemm_smem_bytes(bn, msub, &stages, false);
@@ -499,8 +508,8 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     p.prefetch_b = (l2_prefetch && static_cast<size_t>(N) * pt.K * 4 > (8u << 20)) ? 1 : 0;
     // partials that go to the workspace stay raw (p.epi is all-zero) even when this part has a
     // single split; finish_splitk_kernel applies the epilogue after summing the slabs
-    if (direct) p.epi = epi;
-    else p.splits = splits[i];
+    if (direct && !raw) p.epi = epi;
+    else if (!direct) p.splits = splits[i];
     const int grid = m_groups * n_tiles * splits[i];       // cluster tiles; launch_tc caps at residency
     if (two_cta) {
       if (!a_mn && b_mn) TRY((launch_tc2<false, true>(h, p, smem, grid, s)));
@@ -512,6 +521,10 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     else if (a_mn && b_mn) TRY((launch_tc<true, true>(h, p, smem, grid, s)));
     else FAIL("gemm: A MN-major with B K-major is not instantiated");
     slab0 += splits[i];
+  }
+  if (raw) {
+    *raw_slabs = direct ? 0 : total_splits;
+    return 0;
   }
   if (!direct) {
     TRY(launch_finish(h, h->splitws, slab, total_splits, D, ldd, M, N, epi, s));
@@ -650,7 +663,8 @@ void wgan_destroy(wgan_handle* h) {
     cudaFree(h->powers[n]);
   }
   float* bufs[] = {h->zbuf, h->gh1, h->gh2, h->xcat, h->h1, h->h2, h->d2, h->d1, h->dout, h->v2, h->gd2,
-                   h->gd1, h->dz, h->nsq, h->crow, h->pen, h->norms, h->colpart, h->splitws, h->sample_tmp};
+                   h->gd1, h->dz, h->nsq, h->crow, h->pen, h->norms, h->colpart, h->splitws, h->sample_tmp,
+                   h->gram_k, h->gram_s, h->gram_t};
   for (float* b : bufs) cudaFree(b);
   delete h;
 }
@@ -679,12 +693,14 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   for (int n = 0; n < 2; ++n) { for (int k = 0; k < 4; ++k) h->arena[n][k] = nullptr; h->powers[n] = nullptr; }
   h->zbuf = h->gh1 = h->gh2 = h->xcat = h->h1 = h->h2 = h->d2 = h->d1 = h->dout = h->v2 = h->gd2 = h->gd1 =
       h->dz = h->nsq = h->crow = h->pen = h->norms = h->colpart = h->splitws = h->sample_tmp = nullptr;
+  h->gram_k = h->gram_s = h->gram_t = nullptr;
   auto fail = [&](const std::string& m) { g_create_error = m; wgan_destroy(h); return -1; };
 
   h->Z = cfg->noise_input_size; h->Hg = cfg->inflate_to_size; h->G = cfg->gex_size;
   h->Hd = cfg->disc_internal_size; h->R = cfg->max_batch;
   if (h->Z <= 0 || h->Hg <= 0 || h->G <= 0 || h->Hd <= 0 || h->R <= 0) return fail("non-positive dimension in config");
   if (cfg->gemm_mode != 0 && cfg->gemm_mode != 1) return fail("gemm_mode must be 0 (TF32 tcgen05) or 1 (FP32 verify)");
+  if (cfg->gp_form != 0 && cfg->gp_form != 1) return fail("gp_form must be 0 (explicit chain) or 1 (Gram form)");
   h->Zl = round4(h->Z); h->Hgl = round4(h->Hg); h->Gl = round4(h->G); h->Hdl = round4(h->Hd);
 
   int ndev = 0;
@@ -752,7 +768,9 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
       {&h->dout, 3 * R}, {&h->v2, R * h->Hdl}, {&h->gd2, R * h->Hgl}, {&h->gd1, R * h->Hgl}, {&h->dz, R * h->Zl},
       {&h->nsq, static_cast<size_t>(h->nsq_tiles_max) * R}, {&h->crow, R}, {&h->pen, R}, {&h->norms, R},
       {&h->colpart, static_cast<size_t>(3) * h->colpart_stride},
-      {&h->sample_tmp, R * h->Gl}};
+      {&h->sample_tmp, R * h->Gl},
+      {&h->gram_k, static_cast<size_t>(h->Hd) * h->Hdl}, {&h->gram_s, static_cast<size_t>(h->Hd) * h->Hdl},
+      {&h->gram_t, R * h->Hdl}};
   for (auto& a : allocs) {
     if (cudaMalloc(a.p, (a.n + 64) * 4) != cudaSuccess) return fail("cudaMalloc(workspace) failed (max_batch too large?)");
     cudaMemset(*a.p, 0, (a.n + 64) * 4);
@@ -846,10 +864,18 @@ static int critic_phase_a(wgan_handle* h, const float* x_dev, int ldx, const flo
   const bool gp = h->cfg.lambda_gp != 0.0f;
   const int Bl = rows, nh = gp ? 1 : 0;
   const int G = h->G, Gl = h->Gl;
-  const int real0 = (1 + nh) * Bl;
+  const bool gram = gp && h->cfg.gp_form == 1;
+  const int real0 = gram ? Bl : (1 + nh) * Bl;
   const float* z; int lz;
   TRY(stage_input(h, z_dev, ldz, Bl, h->Z, h->zbuf, h->Zl, &z, &lz, s));
   float* xreal_slot = h->xcat + static_cast<size_t>(real0) * Gl;
+  if (gram) {
+    // Gram form: rows [fake | real] are one stacked operand; x^ is never formed
+    if (x_dev != xreal_slot || ldx != Gl)
+      CK(cudaMemcpy2DAsync(xreal_slot, static_cast<size_t>(Gl) * 4, x_dev, static_cast<size_t>(ldx) * 4,
+                           static_cast<size_t>(G) * 4, Bl, cudaMemcpyDeviceToDevice, s));
+    return generator_forward(h, z, lz, Bl, h->xcat, Gl, s);
+  }
   const float* x; int lx;
   TRY(stage_input(h, x_dev, ldx, Bl, G, xreal_slot, Gl, &x, &lx, s));
   float* xt = h->xcat;
@@ -865,6 +891,86 @@ static int critic_phase_a(wgan_handle* h, const float* x_dev, int ldx, const flo
           x, lx, xt, Gl, eps_dev, xh, Gl, Bl, Gl / 4);
       TRY(post_launch(h, "blend_kernel"));
     }
+  }
+  return 0;
+}
+
+// Critic gradients with the penalty in Gram form (cfg.gp_form == 1; SURVEY 8d shortcuts i + ii).  Same
+// loss and gradients as the explicit chain in real arithmetic; every product with the gene dimension on
+// the interpolate rows is replaced by one with K = W1^T W1 or S = (c g1)^T g1 [Hd, Hd]:
+//   a1(x^) = eps a1(x) + (1 - eps) a1(x~)            (layer 1 is linear before its activation)
+//   n_b^2  = g1_b K g1_b^T,   v1 = c (g1 K) . s1,    dW1 += W1 S
+// Stacked row order here: [fake | real | interpolate]; x~ and x are rows [0, 2 Bl) of xcat.
+static int critic_grads_gram(wgan_handle* h, const float* eps_dev, int Bl, int global_batch, cudaStream_t s) {
+  const int T = 3 * Bl, T2 = 2 * Bl;
+  const int Hd = h->Hd, Hdl = h->Hdl, G = h->G, Gl = h->Gl;
+  const float a = h->cfg.alpha, invB = 1.0f / static_cast<float>(global_batch);
+  const float* W1 = h->P(T_W1); const int ldw1 = h->td[T_W1].ld;
+  const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
+  const size_t hat0 = static_cast<size_t>(T2) * Hdl;
+  float* h1_hat = h->h1 + hat0;
+  float* h2_hat = h->h2 + hat0;
+  float* g1 = h->d1 + hat0;
+
+  // layer 1: raw products of [fake; real], then bias + activation + the interpolate's blend  [W:107-111]
+  {
+    int slabs = 0;
+    Part p1{h->xcat, Gl, W1, ldw1, G};
+    TRY(run_gemm(h, false, true, &p1, 1, h->h1, Hdl, T2, Hd, epi_none(), nullptr, 0, s, nullptr, 0, &slabs, false));
+    const float* part = slabs > 0 ? h->splitws : h->h1;
+    const size_t n = static_cast<size_t>(Bl) * ((Hd + 3) / 4);
+    KLAUNCH(l1_gram_finish_kernel, ew_grid(n, 256, h->num_sms), 256, 0, s, part,
+            round64(static_cast<size_t>(T2) * Hdl), slabs > 0 ? slabs : 1, h->h1, Hdl, Bl, Hd, h->P(T_B1), eps_dev, a);
+    TRY(post_launch(h, "l1_gram_finish_kernel"));
+  }
+  // layer 2, layer 3 + upstream deltas (fake +1/B, real -1/B, interpolate g2 = w3 . s2)  [W:113-123,137]
+  TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, T, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
+  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(T) * 32, 256, h->num_sms), 256, 0, s,
+      h->h2, Hdl, T, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, invB, -invB, 1.0f, a);
+  TRY(post_launch(h, "critic_head_kernel"));
+  TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, T, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
+
+  // K = W1^T W1, T = g1 K, per-row norm / coefficient, v1 (over h1_hat), T <- c g1
+  TRY(gemm1(h, true, true, W1, ldw1, W1, ldw1, h->gram_k, Hdl, Hd, Hd, G, epi_none(), s));
+  TRY(gemm1(h, false, true, g1, Hdl, h->gram_k, Hdl, h->gram_t, Hdl, Bl, Hd, Hd, epi_none(), s));
+  h->last_gx_rows = Bl;
+  KLAUNCH(gp_coef_gram_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s,
+      h->gram_t, g1, h1_hat, Hdl, Bl, Hd, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, a);
+  TRY(post_launch(h, "gp_coef_gram_kernel"));
+  float* sc = h->scalars(WGAN_NET_CRITIC);
+  SumJob sums[3] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + Bl, sc + WGAN_S_DREAL, Bl, invB},
+                    {h->pen, sc + WGAN_S_GP, Bl, h->cfg.lambda_gp * invB}};
+  TRY(segment_sums(h, sums, 3, s));
+  // v2 = (v1 W2) . s2
+  TRY(gemm1(h, false, true, h1_hat, Hdl, W2, ldw2, h->v2, Hdl, Bl, Hd, Hd, epi_mask(h2_hat, Hdl, a), s));
+  // S = (c g1)^T g1
+  TRY(gemm1(h, true, true, h->gram_t, Hdl, g1, Hdl, h->gram_s, Hdl, Hd, Hd, Bl, epi_none(), s));
+
+  // dW1 = W1 S + [x~; x]^T [delta1_fake; delta1_real]: raw slabs of both products, one finish pass
+  {
+    int s0 = 0, s1 = 0;
+    Part ps{W1, ldw1, h->gram_s, Hdl, Hd};
+    TRY(run_gemm(h, false, true, &ps, 1, h->Gr(T_W1), ldw1, G, Hd, epi_none(), nullptr, 0, s, nullptr, 0, &s0, true));
+    Part pw{h->xcat, Gl, h->d1, Hdl, T2};
+    TRY(run_gemm(h, true, true, &pw, 1, h->Gr(T_W1), ldw1, G, Hd, epi_none(), nullptr, 0, s, nullptr, s0, &s1, true));
+    TRY(launch_finish(h, h->splitws, round64(static_cast<size_t>(G) * ldw1), s0 + s1, h->Gr(T_W1), ldw1, G, Hd,
+                      epi_none(), s));
+  }
+  // dW2 = [h1_fake; h1_real; v1]^T [delta2_fake; delta2_real; g2]
+  TRY(gemm1(h, true, true, h->h1, Hdl, h->d2, Hdl, h->Gr(T_W2), ldw2, Hd, Hd, T, epi_none(), s));
+  {
+    ColsumJob jobs[3];
+    memset(jobs, 0, sizeof jobs);
+    jobs[0].seg[0] = ColsumSeg{h->d1, T2, Hdl, 1.0f};
+    jobs[0].nseg = 1; jobs[0].N = Hd; jobs[0].out = h->Gr(T_B1);
+    jobs[1].seg[0] = ColsumSeg{h->d2, T2, Hdl, 1.0f};
+    jobs[1].nseg = 1; jobs[1].N = Hd; jobs[1].out = h->Gr(T_B2);
+    jobs[2].seg[0] = ColsumSeg{h->h2, Bl, Hdl, invB};
+    jobs[2].seg[1] = ColsumSeg{h->h2 + static_cast<size_t>(Bl) * Hdl, Bl, Hdl, -invB};
+    jobs[2].seg[2] = ColsumSeg{h->v2, Bl, Hdl, 1.0f};
+    jobs[2].nseg = 3; jobs[2].N = Hd; jobs[2].out = h->Gr(T_W3);
+    TRY(colsum_jobs(h, jobs, 3, s));
+    CK(cudaMemsetAsync(h->Gr(T_B3), 0, 4, s));
   }
   return 0;
 }
@@ -898,6 +1004,7 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   const bool prepared = (h->prep_x == x_dev && h->prep_z == z_dev && h->prep_eps == eps_dev && h->prep_rows == rows);
   h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
   if (!prepared) TRY(critic_phase_a(h, x_dev, ldx, z_dev, ldz, eps_dev, rows, s));
+  if (gp && h->cfg.gp_form == 1) return critic_grads_gram(h, eps_dev, rows, global_batch, s);
   // where phase A left the inputs
   float* xreal_slot = h->xcat + static_cast<size_t>(real0) * Gl;
   const bool x_legal = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && (ldx & 3) == 0;
@@ -1241,7 +1348,9 @@ int wgan_get_buffer(wgan_handle* h, const char* name, float** dev_ptr, int* rows
   const int Bl = h->last_gx_rows;
   std::string n(name);
   if (n == "x_tilde") { *dev_ptr = h->xcat; *rows = h->R; *cols = h->G; *ld = h->Gl; }
-  else if (n == "gx") { *dev_ptr = h->xcat + static_cast<size_t>(Bl) * h->Gl; *rows = Bl; *cols = h->G; *ld = h->Gl; }
+  else if (n == "gx") {
+    if (h->cfg.lambda_gp != 0.0f && h->cfg.gp_form == 1) FAIL("get_buffer: the Gram form never materialises gx");
+    *dev_ptr = h->xcat + static_cast<size_t>(Bl) * h->Gl; *rows = Bl; *cols = h->G; *ld = h->Gl; }
   else if (n == "xcat") { *dev_ptr = h->xcat; *rows = 3 * h->R; *cols = h->G; *ld = h->Gl; }
   else if (n == "norms") { *dev_ptr = h->norms; *rows = 1; *cols = Bl; *ld = Bl; }
   else if (n == "d") { *dev_ptr = h->dout; *rows = 1; *cols = 3 * h->R; *ld = 3 * h->R; }

@@ -284,6 +284,89 @@ __global__ void gp_coef_kernel(const float* __restrict__ nsq, int ntiles, int ti
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gram form of the penalty (shortcuts i + ii; exact in real arithmetic).
+//
+// l1_gram_finish_kernel: critic layer 1 is linear before its activation, so the interpolate's
+// pre-activation is the blend of the two that are computed anyway:
+//   a_f = x~ W1, a_r = x W1 (raw products, `splits` slabs of [2B, ld], fake rows first)
+//   h1[b]      = lrelu(a_f + b1)              h1[B + b] = lrelu(a_r + b1)
+//   h1[2B + b] = lrelu(eps_b a_r + (1 - eps_b) a_f + b1)
+// `part` may alias `h1` (splits == 1, products written in place): a thread reads its own two
+// float4 groups before it writes.
+// ---------------------------------------------------------------------------------------------
+__global__ void l1_gram_finish_kernel(const float* part, size_t slab_stride, int splits, float* h1, int ld,
+                                      int B, int N, const float* __restrict__ bias,
+                                      const float* __restrict__ eps, float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n4 = (N + 3) >> 2;
+  const size_t total = static_cast<size_t>(B) * n4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / n4), n = static_cast<int>(i % n4) * 4;
+    const size_t off_f = static_cast<size_t>(b) * ld + n;
+    const size_t off_r = off_f + static_cast<size_t>(B) * ld;
+    const size_t off_h = off_r + static_cast<size_t>(B) * ld;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f), r = f;
+    for (int s = 0; s < splits; ++s) {
+      const float4 tf = *reinterpret_cast<const float4*>(part + s * slab_stride + off_f);
+      const float4 tr = *reinterpret_cast<const float4*>(part + s * slab_stride + off_r);
+      f.x += tf.x; f.y += tf.y; f.z += tf.z; f.w += tf.w;
+      r.x += tr.x; r.y += tr.y; r.z += tr.z; r.w += tr.w;
+    }
+    const float e = eps[b], g = 1.0f - e;
+    const float vf[4] = {f.x, f.y, f.z, f.w}, vr[4] = {r.x, r.y, r.z, r.w};
+    float of[4], orr[4], oh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j >= N) { of[j] = orr[j] = oh[j] = 0.0f; continue; }
+      const float bj = bias[n + j];
+      const float yf = vf[j] + bj, yr = vr[j] + bj, yh = e * vr[j] + g * vf[j] + bj;
+      of[j] = fmaxf(yf, alpha * yf);
+      orr[j] = fmaxf(yr, alpha * yr);
+      oh[j] = fmaxf(yh, alpha * yh);
+    }
+    *reinterpret_cast<float4*>(h1 + off_f) = make_float4(of[0], of[1], of[2], of[3]);
+    *reinterpret_cast<float4*>(h1 + off_r) = make_float4(orr[0], orr[1], orr[2], orr[3]);
+    *reinterpret_cast<float4*>(h1 + off_h) = make_float4(oh[0], oh[1], oh[2], oh[3]);
+  }
+}
+
+// gp_coef_gram_kernel: with K = W1^T W1 and T = g1 K (both from the tensor-core GEMM),
+//   n_b^2 = g1_b K g1_b^T = T_b . g1_b,   c_b = lambda 2/B (n_b - 1) / n_b,   pen[b] = (n_b - 1)^2
+//   v1    = c (g1 K) . s1      (= c (gx W1) . s1 of the explicit chain), in place over the h1 rows
+//   T    <- c g1               (left operand of S = (c g1)^T g1, the Gram factor of dW1 = W1 S)
+// One warp per interpolate row.
+__global__ void gp_coef_gram_kernel(float* __restrict__ T, const float* __restrict__ g1, float* __restrict__ h1hat,
+                                    int ld, int rows, int H, float two_lambda_over_B, float* __restrict__ c,
+                                    float* __restrict__ pen, float* __restrict__ norms, float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    float* tr = T + static_cast<size_t>(r) * ld;
+    const float* gr = g1 + static_cast<size_t>(r) * ld;
+    float* hr = h1hat + static_cast<size_t>(r) * ld;
+    float acc = 0.0f;
+    for (int j = lane; j < H; j += 32) acc = fmaf(tr[j], gr[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float n = sqrtf(fmaxf(acc, 0.0f));
+    const float cb = two_lambda_over_B * (n - 1.0f) / n;
+    if (lane == 0) {
+      c[r] = cb;
+      pen[r] = (n - 1.0f) * (n - 1.0f);
+      norms[r] = n;
+    }
+    for (int j = lane; j < H; j += 32) {
+      const float t = tr[j], g = gr[j], hh = hr[j];
+      hr[j] = cb * t * ((hh > 0.0f) ? 1.0f : alpha);
+      tr[j] = cb * g;
+    }
+  }
+}
+
 // x_hat[b,:] = eps[b] * x[b,:] + (1 - eps[b]) * x_tilde[b,:]      (SURVEY A.4), float4 over padded rows
 __global__ void blend_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ xt,
                              int ldt, const float* __restrict__ eps, float* __restrict__ xh, int ldh,

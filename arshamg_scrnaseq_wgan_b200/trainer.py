@@ -63,6 +63,8 @@ class WGANConfig:
     epsilon: float = 1e-8               # [A:38]
     alpha: float = 0.2                  # tf.nn.leaky_relu default
     lambda_gp: float = 10.0             # build-defined; 0 => reference-literal
+    gp_form: str = "explicit"           # "explicit": x^ materialised, gx = g1 W1^T;
+                                        # "gram": same penalty through K = W1^T W1 (SURVEY 8d shortcuts)
     n_critic: int = 5                   # build-defined; 1 => reference-literal
     step_order: str = "critic_first"    # "gen_first" => reference-literal [W:196,199]
 
@@ -103,8 +105,11 @@ class WGANTrainer:
             cfg = dataclasses.replace(cfg, learn_rate=optimizer.learning_rate, beta1=optimizer.beta1,
                                       beta2=optimizer.beta2, epsilon=optimizer.epsilon)
             self.cfg = cfg
+        if cfg.gp_form not in ("explicit", "gram"):
+            raise ValueError(f"gp_form must be 'explicit' or 'gram', got {cfg.gp_form!r}")
         c = _lib.WganConfig(cfg.noise_input_size, cfg.inflate_to_size, cfg.gex_size, cfg.disc_internal_size,
-                            self.max_batch, self.device, gemm_mode, 0, cfg.learn_rate, cfg.beta1, cfg.beta2,
+                            self.max_batch, self.device, gemm_mode, 1 if cfg.gp_form == "gram" else 0,
+                            cfg.learn_rate, cfg.beta1, cfg.beta2,
                             cfg.epsilon, cfg.alpha, cfg.lambda_gp, 0.0, 0.0)
         self._h = C.c_void_p()
         rc = self.lib.wgan_create(C.byref(c), C.byref(self._h))
@@ -361,11 +366,12 @@ class WGANTrainer:
         self._data = buf
 
     def real_slot(self, rows: int) -> torch.Tensor:
-        """The rows of the library's stacked activation buffer [fake | interpolate | real] where the
-        critic step expects the real cells; gathering straight into it lets layer 1 and its weight
-        gradient run as single GEMMs over the stacked rows (no staging copy)."""
+        """The rows of the library's stacked activation buffer ([fake | interpolate | real], or
+        [fake | real] without a penalty and in the Gram form) where the critic step expects the real
+        cells; gathering straight into it lets layer 1 and its weight gradient run as single GEMMs
+        over the stacked rows (no staging copy)."""
         xcat = self.buffer("xcat")
-        r0 = (2 if self.cfg.lambda_gp != 0 else 1) * rows
+        r0 = (2 if (self.cfg.lambda_gp != 0 and self.cfg.gp_form == "explicit") else 1) * rows
         return xcat[r0:r0 + rows]
 
     def gather(self, idx: torch.Tensor) -> torch.Tensor:

@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gp-form", default="explicit", choices=["explicit", "gram"],
+                    help="penalty evaluation of the headline run (the Gram form is also timed as `gram_form`)")
+    ap.add_argument("--no-gram", action="store_true")
     return ap.parse_args()
 
 
@@ -299,7 +302,7 @@ def run_b200(args):
 
     from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer, _lib
     _lib.build()
-    cfg = WGANConfig(lambda_gp=10.0, n_critic=5)
+    cfg = WGANConfig(lambda_gp=10.0, n_critic=5, gp_form=args.gp_form)
     B = args.batch
     tr = WGANTrainer(cfg, max_batch=max(B, 32768), device=local)
     tr.init_params(seed=0)
@@ -400,6 +403,43 @@ def run_b200(args):
                "tensor_tflops": cells_per_s * FLOP_GEN_FWD / 1e12,
                "output_gbs": cells_per_s * cfg.gex_size * 4 / 1e9}
 
+    # ---------------- the same iteration with the penalty in Gram form (reported separately) ----------------
+    # layer-1 pre-activation blend + K = W1^T W1 give the same loss and gradients in real arithmetic
+    # with ~30 % fewer FLOPs and no x^ / gx traffic.  `value` above stays on the explicit chain (the FLOP table's
+    # denominator); this is the number a user gets with WGANConfig(gp_form="gram").
+    gram = None
+    if not args.no_gram and cfg.gp_form == "explicit":
+        tg = WGANTrainer(WGANConfig(lambda_gp=10.0, n_critic=5, gp_form="gram"), max_batch=B, device=local)
+        tg.init_params(seed=0)
+        tg._data = tr._data
+        for it in range(max(args.warmup - 1, 0)):
+            tg.train_iteration_resident(it, B, seed=0)
+        greplay = tg.capture_iteration(B, seed=0, start_it=max(args.warmup - 1, 0))
+        for _ in range(2):
+            greplay()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for it in range(args.steps):
+            greplay()
+        g1.record()
+        barrier()
+        tg_ms = torch.tensor([g0.elapsed_time(g1)], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tg_ms, op=dist.ReduceOp.MAX)
+        g_ms_step = float(tg_ms.item()) / args.steps
+        gram = {"value": world * 1000.0 / g_ms_step, "unit": UNIT, "ms_per_step": g_ms_step,
+                "gpu_launches": int(tg.graph_launches_per_replay * args.steps),
+                "config": "same workload, WGANConfig(gp_form='gram'): penalty through K = W1^T W1 (SURVEY 8d shortcuts i+ii)",
+                "losses": tg.train_iteration_resident(args.warmup + args.steps + 8, B, seed=0, read=True)}
+        if not args.no_e2e:
+            dt_g, out_g = timed(lambda: tg.train_iteration_host_indices_graph(idxs, zs[:nb], es, zs[nb]))
+            gram["e2e"] = {"value": world * args.steps / dt_g, "unit": UNIT, "ms_per_step": dt_g / args.steps * 1e3,
+                           "h2d_bytes_per_step": h2d_i, "d2h_bytes_per_step": 32, "last": out_g}
+        tg._graph_keepalive = None
+        tg._hgraph = None
+        torch.cuda.synchronize()
+
     roof = cpu = None
     if rank == 0:
         roof = dominant_kernel_roofline(tr, B, torch, pk)
@@ -411,13 +451,14 @@ def run_b200(args):
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
                 "config": {"workload": "BASELINE config 2: WGAN-GP iteration, reference dims 100-600-600-6605 / "
-                                       f"6605-200-200-1, per-GPU batch {B} (global {B * world}), n_critic 5, lambda 10, "
+                                       f"6605-200-200-1, per-GPU batch {B} (global {B * world}), n_critic 5, lambda 10 "
+                                       f"(penalty: {cfg.gp_form} form), "
                                        "TF-Adam lr 1e-5, synthetic lTPM 1500x6605 resident in HBM, device Philox RNG + gather, "
                                        "iteration replayed as one CUDA graph",
                            "parallelism": f"dp{world}", "l2": "per-step working set 325 MB > 126 MB L2 (inputs larger than L2)",
                            "iteration_tflops": world * B * FLOP_PER_SAMPLE_ITER / (ms_step * 1e-3) / 1e12},
                 "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-                "sampler": sampler, "losses": last}
+                "sampler": sampler, "gram_form": gram, "losses": last}
         print(json.dumps(line), flush=True)
     # Teardown.  Captured graphs hold NCCL kernels: drop them before the communicator, and never let a
     # wedged collective teardown keep the job (and the GPUs) alive after the result line is out.

@@ -40,7 +40,9 @@ typedef struct wgan_config {
   int32_t max_batch;          /* largest per-GPU batch (rows) any call will use */
   int32_t device;             /* CUDA device ordinal */
   int32_t gemm_mode;          /* 0 = TF32 tcgen05, 1 = FP32 CUDA cores (verification) */
-  int32_t reserved0;
+  int32_t gp_form;            /* gradient-penalty evaluation: 0 = explicit chain (x^ materialised),
+                                 1 = Gram form (same value in real arithmetic: layer-1 pre-activation blend and
+                                 K = W1^T W1, SURVEY 8d shortcuts i + ii); ignored when lambda_gp == 0 */
   float learn_rate;           /* [W:22] 1e-5 */
   float beta1;                /* [W:154-155] 0.9 */
   float beta2;                /* [W:154-155] 0.999 */
