@@ -62,6 +62,8 @@ SIGNATURES = {
     "wgan_rng_indices": (_I, [_P, C.c_int64, _I, C.c_uint32, C.c_uint64, C.c_uint32, _P, _P]),
     "wgan_counter_add": (_I, [_P, C.c_uint32, _P]),
     "wgan_gather_rows": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
+    "wgan_draw_minibatch": (_I, [_P, _I, C.c_uint32, _P, _I, _I, _P, _I, _I, _F, _P, _P, C.c_int64, _I, C.c_uint64,
+                                 C.c_uint32, _P, _P]),
     "wgan_gemm": (_I, [_P, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P,
                        C.POINTER(_I), _I, _P]),
     "wgan_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),

@@ -558,8 +558,11 @@ int gemm1(wgan_handle* h, bool a_mn, bool b_mn, const float* A, int lda, const f
   return run_gemm(h, a_mn, b_mn, &p, 1, D, ldd, M, N, e, sumsq_tiles, 0, s);
 }
 
-// Up to three column-sum jobs in one launch pair: out_j[n] = sum_seg scale * sum_r X_seg[r, n].
-int colsum_jobs(wgan_handle* h, const ColsumJob* jobs, int njobs, cudaStream_t s) {
+// Up to three column-sum jobs in one launch pair: out_j[n] = sum_seg scale * sum_r X_seg[r, n].  `zero_out`
+// (optional) is one extra float to clear; `sums` (optional) are loss-scalar sums evaluated by extra blocks of the
+// first launch.
+int colsum_jobs(wgan_handle* h, const ColsumJob* jobs, int njobs, cudaStream_t s, float* zero_out = nullptr,
+                const SumJob* sums = nullptr, int nsums = 0) {
   ColsumArgs a;
   memset(&a, 0, sizeof a);
   int maxrows = 1, maxN = 1;
@@ -573,28 +576,19 @@ int colsum_jobs(wgan_handle* h, const ColsumJob* jobs, int njobs, cudaStream_t s
   if (RC > 64) RC = 64;
   if (RC < 1) RC = 1;
   a.part_stride = h->colpart_stride;
-  dim3 grid(cdiv(maxN, 32), RC, njobs);
-  KLAUNCH(colsum_partial_kernel, grid, 256, 0, s, a, h->colpart);
+  a.njobs = njobs;
+  a.RC = RC;
+  a.zero_out = zero_out;
+  for (int j = 0; j < 3; ++j) a.block0[j + 1] = a.block0[j] + (j < njobs ? cdiv(jobs[j].N, 32) * RC : 0);
+  SumJobs sj;
+  memset(&sj, 0, sizeof sj);
+  for (int j = 0; j < nsums; ++j) sj.job[j] = sums[j];
+  const int grid = a.block0[njobs] + nsums;
+  KLAUNCH(colsum_partial_kernel, grid, 256, 0, s, a, h->colpart, sj, nsums);
   TRY(post_launch(h, "colsum_partial_kernel"));
   dim3 g2(cdiv(maxN, 256), njobs);
   KLAUNCH(colsum_final_kernel, g2, 256, 0, s, a, h->colpart, RC);
   return post_launch(h, "colsum_final_kernel");
-}
-
-int colsum(wgan_handle* h, const ColsumSeg* segs, int nseg, int N, float* out, cudaStream_t s) {
-  ColsumJob jb;
-  memset(&jb, 0, sizeof jb);
-  for (int i = 0; i < nseg; ++i) jb.seg[i] = segs[i];
-  jb.nseg = nseg; jb.N = N; jb.out = out;
-  return colsum_jobs(h, &jb, 1, s);
-}
-
-int segment_sums(wgan_handle* h, const SumJob* jobs, int njobs, cudaStream_t s) {
-  SumJobs a;
-  memset(&a, 0, sizeof a);
-  for (int j = 0; j < njobs; ++j) a.job[j] = jobs[j];
-  KLAUNCH(segment_sum_kernel, njobs, 1024, 0, s, a);
-  return post_launch(h, "segment_sum_kernel");
 }
 
 // Bring a caller matrix into a TMA-legal layout (16 B aligned, ld % 4 == 0); copies only if needed.
@@ -937,10 +931,6 @@ static int critic_grads_gram(wgan_handle* h, const float* eps_dev, int Bl, int g
   KLAUNCH(gp_coef_gram_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s,
       h->gram_t, g1, h1_hat, Hdl, Bl, Hd, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, a);
   TRY(post_launch(h, "gp_coef_gram_kernel"));
-  float* sc = h->scalars(WGAN_NET_CRITIC);
-  SumJob sums[3] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + Bl, sc + WGAN_S_DREAL, Bl, invB},
-                    {h->pen, sc + WGAN_S_GP, Bl, h->cfg.lambda_gp * invB}};
-  TRY(segment_sums(h, sums, 3, s));
   // v2 = (v1 W2) . s2
   TRY(gemm1(h, false, true, h1_hat, Hdl, W2, ldw2, h->v2, Hdl, Bl, Hd, Hd, epi_mask(h2_hat, Hdl, a), s));
   // S = (c g1)^T g1
@@ -969,8 +959,11 @@ static int critic_grads_gram(wgan_handle* h, const float* eps_dev, int Bl, int g
     jobs[2].seg[1] = ColsumSeg{h->h2 + static_cast<size_t>(Bl) * Hdl, Bl, Hdl, -invB};
     jobs[2].seg[2] = ColsumSeg{h->v2, Bl, Hdl, 1.0f};
     jobs[2].nseg = 3; jobs[2].N = Hd; jobs[2].out = h->Gr(T_W3);
-    TRY(colsum_jobs(h, jobs, 3, s));
-    CK(cudaMemsetAsync(h->Gr(T_B3), 0, 4, s));
+    // d b3 = sum(+1/B) + sum(-1/B) over equal row counts = 0; loss scalars: mean parts of D_fake / D_real, penalty
+    float* sc = h->scalars(WGAN_NET_CRITIC);
+    const SumJob sums[3] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + Bl, sc + WGAN_S_DREAL, Bl, invB},
+                            {h->pen, sc + WGAN_S_GP, Bl, h->cfg.lambda_gp * invB}};
+    TRY(colsum_jobs(h, jobs, 3, s, h->Gr(T_B3), sums, 3));
   }
   return 0;
 }
@@ -1026,11 +1019,10 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
   TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, T, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
   // layer 3 + upstream deltas  [W:119-123,137]
-  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(T) * 32, 256, h->num_sms), 256, 0, s, 
+  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(T) * 32, 256, h->num_sms), 256, 0, s,
       h->h2, Hdl, T, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, invB, gp ? 1.0f : -invB,
       gp ? -invB : 0.0f, a);
   TRY(post_launch(h, "critic_head_kernel"));
-  float* sc = h->scalars(WGAN_NET_CRITIC);
   // delta1 / g1 = (delta2 W2^T) . slope(h1)
   TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, T, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
 
@@ -1045,21 +1037,14 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
     TRY(gemm1(h, false, false, d1_hat, Hdl, W1, ldw1, xh, Gl, Bl, G, Hd, eg, s, &tiles));
     h->last_gx_rows = Bl;
     // norm, penalty, per-row coefficient; g1 <- c . g1
-    KLAUNCH(gp_coef_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s, 
+    KLAUNCH(gp_coef_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s,
         h->nsq, tiles, Bl, Bl, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, d1_hat, Hdl, Hd);
     TRY(post_launch(h, "gp_coef_kernel"));
-    SumJob jobs[3] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + real0, sc + WGAN_S_DREAL, Bl, invB},
-                      {h->pen, sc + WGAN_S_GP, Bl, h->cfg.lambda_gp * invB}};
-    TRY(segment_sums(h, jobs, 3, s));                    // loss scalars: mean parts of D_fake / D_real, penalty
     // parameter-gradient-of-norm pass: v1 = c . (gx W1) . s1 (in place over h1_hat), v2 = (v1 W2) . s2
     EpiParams ev1 = epi_mask(h1_hat, Hdl, a);
     ev1.row_scale = h->crow;
     TRY(gemm1(h, false, true, xh, Gl, W1, ldw1, h1_hat, Hdl, Bl, Hd, G, ev1, s));
     TRY(gemm1(h, false, true, h1_hat, Hdl, W2, ldw2, h->v2, Hdl, Bl, Hd, Hd, epi_mask(h2_hat, Hdl, a), s));
-  } else {
-    SumJob jobs[2] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + real0, sc + WGAN_S_DREAL, Bl, invB}};
-    TRY(segment_sums(h, jobs, 2, s));
-    CK(cudaMemsetAsync(sc + WGAN_S_GP, 0, 4, s));
   }
 
   // weight gradients
@@ -1090,8 +1075,12 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
     jobs[2].seg[1] = ColsumSeg{h->h2 + static_cast<size_t>(real0) * Hdl, Bl, Hdl, -invB};
     jobs[2].seg[2] = ColsumSeg{h->v2, Bl, Hdl, 1.0f};
     jobs[2].nseg = gp ? 3 : 2; jobs[2].N = Hd; jobs[2].out = h->Gr(T_W3);
-    TRY(colsum_jobs(h, jobs, 3, s));
-    CK(cudaMemsetAsync(h->Gr(T_B3), 0, 4, s));           // sum(+1/B) + sum(-1/B) over equal row counts
+    // d b3 = sum(+1/B) + sum(-1/B) over equal row counts = 0; loss scalars: mean parts of D_fake / D_real and the
+    // penalty (an empty sum clears it when there is none)
+    float* sc = h->scalars(WGAN_NET_CRITIC);
+    const SumJob sums[3] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + real0, sc + WGAN_S_DREAL, Bl, invB},
+                            {h->pen, sc + WGAN_S_GP, gp ? Bl : 0, h->cfg.lambda_gp * invB}};
+    TRY(colsum_jobs(h, jobs, 3, s, h->Gr(T_B3), sums, 3));
   }
   return 0;
 }
@@ -1110,8 +1099,9 @@ static int generator_phase_a(wgan_handle* h, const float* z_dev, int ldz, int ro
   // z is later the MN-major A operand of the first-layer weight gradient: the last 32-column chunk of an
   // MN-major tile may read up to 124 B past a row, which the engine's own buffers tolerate (slack) but a
   // caller's tensor need not -- always work on the staged copy (1.6 MB at batch 4096)
-  CK(cudaMemcpy2DAsync(h->zbuf, static_cast<size_t>(h->Zl) * 4, z_dev, static_cast<size_t>(ldz) * 4,
-                       static_cast<size_t>(h->Z) * 4, rows, cudaMemcpyDeviceToDevice, s));
+  KLAUNCH(copy2d_kernel, ew_grid(static_cast<size_t>(rows) * h->Z, 256, h->num_sms), 256, 0, s, z_dev, ldz, h->zbuf,
+          h->Zl, rows, h->Z);
+  TRY(post_launch(h, "copy2d_kernel"));
   return generator_forward(h, h->zbuf, h->Zl, rows, h->xcat, h->Gl, s);
 }
 
@@ -1146,12 +1136,9 @@ int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, 
   const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
   TRY(gemm1(h, false, true, xt, Gl, W1, ldw1, h->h1, Hdl, Bl, Hd, G, epi_bias_lrelu(h->P(T_B1), a), s));
   TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, Bl, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
-  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s, 
+  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s,
       h->h2, Hdl, Bl, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, -invB, 0.f, 0.f, a);
   TRY(post_launch(h, "critic_head_kernel"));
-  float* sc = h->scalars(WGAN_NET_GENERATOR);
-  SumJob gj = {h->dout, sc + WGAN_S_DFAKE, Bl, invB};
-  TRY(segment_sums(h, &gj, 1, s));
   // back through the critic to the generated cells
   TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, Bl, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
   TRY(gemm1(h, false, false, h->d1, Hdl, W1, ldw1, d3, Gl, Bl, G, Hd, epi_mask(xt, Gl, a), s));
@@ -1159,16 +1146,24 @@ int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, 
   const float* Wg3 = h->P(T_WG3); const int ldg3 = h->td[T_WG3].ld;
   const float* Wg2 = h->P(T_WG2); const int ldg2 = h->td[T_WG2].ld;
   TRY(gemm1(h, true, true, h->gh2, Hgl, d3, Gl, h->Gr(T_WG3), ldg3, Hg, G, Bl, epi_none(), s));
-  ColsumSeg c3[3] = {{d3, Bl, Gl, 1.0f}, {}, {}};
-  TRY(colsum(h, c3, 1, G, h->Gr(T_BG3), s));
   TRY(gemm1(h, false, false, d3, Gl, Wg3, ldg3, h->gd2, Hgl, Bl, Hg, G, epi_mask(h->gh2, Hgl, a), s));
   TRY(gemm1(h, true, true, h->gh1, Hgl, h->gd2, Hgl, h->Gr(T_WG2), ldg2, Hg, Hg, Bl, epi_none(), s));
-  ColsumSeg c2[3] = {{h->gd2, Bl, Hgl, 1.0f}, {}, {}};
-  TRY(colsum(h, c2, 1, Hg, h->Gr(T_BG2), s));
   TRY(gemm1(h, false, false, h->gd2, Hgl, Wg2, ldg2, h->gd1, Hgl, Bl, Hg, Hg, epi_mask(h->gh1, Hgl, a), s));
   TRY(gemm1(h, true, true, z, lz, h->gd1, Hgl, h->Gr(T_WG1), h->td[T_WG1].ld, h->Z, Hg, Bl, epi_none(), s));
-  ColsumSeg c1[3] = {{h->gd1, Bl, Hgl, 1.0f}, {}, {}};
-  TRY(colsum(h, c1, 1, Hg, h->Gr(T_BG1), s));
+  {
+    // the three bias gradients (column sums of the layer deltas) in one launch
+    ColsumJob jobs[3];
+    memset(jobs, 0, sizeof jobs);
+    jobs[0].seg[0] = ColsumSeg{d3, Bl, Gl, 1.0f};
+    jobs[0].nseg = 1; jobs[0].N = G; jobs[0].out = h->Gr(T_BG3);
+    jobs[1].seg[0] = ColsumSeg{h->gd2, Bl, Hgl, 1.0f};
+    jobs[1].nseg = 1; jobs[1].N = Hg; jobs[1].out = h->Gr(T_BG2);
+    jobs[2].seg[0] = ColsumSeg{h->gd1, Bl, Hgl, 1.0f};
+    jobs[2].nseg = 1; jobs[2].N = Hg; jobs[2].out = h->Gr(T_BG1);
+    float* sc = h->scalars(WGAN_NET_GENERATOR);
+    const SumJob gj = {h->dout, sc + WGAN_S_DFAKE, Bl, invB};          // mean D(G(z)) for obj_g [W:138]
+    TRY(colsum_jobs(h, jobs, 3, s, nullptr, &gj, 1));
+  }
   return 0;
 }
 
@@ -1323,6 +1318,27 @@ int wgan_gather_rows(const float* data_dev, int ld_data, const int64_t* idx_dev,
   KLAUNCH(gather_rows_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), data_dev, ld_data, idx_dev, out_dev,
                                                                            ld_out, rows, cols4);
   return rng_launch_check("gather_rows_kernel");
+}
+
+int wgan_draw_minibatch(const float* data_dev, int ld_data, uint32_t n_cells, float* x_out_dev, int ld_out, int cols,
+                        float* z_out_dev, int ldz, int dim, float sigma, float* eps_out_dev, int64_t* idx_out_dev,
+                        int64_t row0, int rows, uint64_t seed, uint32_t call_id, const uint32_t* call_id_dev,
+                        wgan_stream_t stream) {
+  if (!data_dev || !x_out_dev || !z_out_dev || rows <= 0 || cols <= 0 || dim <= 0 || n_cells == 0 || ldz < dim) {
+    g_create_error = "draw_minibatch: bad argument";
+    return -2;
+  }
+  if ((ld_data & 3) || (ld_out & 3) || (reinterpret_cast<uintptr_t>(data_dev) & 15) ||
+      (reinterpret_cast<uintptr_t>(x_out_dev) & 15) || round4(cols) > ld_data || round4(cols) > ld_out) {
+    g_create_error = "draw_minibatch: data and x_out must be 16-byte aligned with ld % 4 == 0 and ld >= padded cols";
+    return -2;
+  }
+  if (upload_poisson_cdf_once() != 0) { g_create_error = "draw_minibatch: constant upload failed"; return -1; }
+  const int grid = rows < 148 * 16 ? rows : 148 * 16;
+  KLAUNCH(draw_minibatch_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), data_dev, ld_data, n_cells, x_out_dev,
+          ld_out, round4(cols) / 4, z_out_dev, ldz, dim, sigma, eps_out_dev, idx_out_dev, static_cast<long>(row0), rows,
+          seed, call_id, call_id_dev);
+  return rng_launch_check("draw_minibatch_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -198,6 +198,18 @@ gemm_fp32_kernel(const float* __restrict__ A, long sam, long sak, const float* _
   }
 }
 
+// Deterministic sums for the loss scalars: out_j[0] = scale_j * sum(ptr_j[0..n_j)); a job with n == 0 writes 0.
+// They ride along as extra blocks of the column-sum launch (see colsum_partial_kernel).
+struct SumJob {
+  const float* ptr;
+  float* out;
+  int n;
+  float scale;
+};
+struct SumJobs {
+  SumJob job[3];
+};
+
 // ---------------------------------------------------------------------------------------------
 // Critic head.  One warp per row r of h2 [rows, ld]:
 //   d[r]     = h2[r,:] . w3 + b3                                   [W:119-123]
@@ -229,39 +241,10 @@ __global__ void critic_head_kernel(const float* __restrict__ h2, int ld, int row
   }
 }
 
-// Deterministic block sums: job j (= blockIdx.x) writes out_j[0] = scale_j * sum(ptr_j[0..n_j)).
-struct SumJob {
-  const float* ptr;
-  float* out;
-  int n;
-  float scale;
-};
-struct SumJobs {
-  SumJob job[3];
-};
-__global__ void __launch_bounds__(1024) segment_sum_kernel(SumJobs jobs) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float red[32];
-  const SumJob jb = jobs.job[blockIdx.x];
-  float acc = 0.0f;
-  for (int i = threadIdx.x; i < jb.n; i += blockDim.x) acc += jb.ptr[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) jb.out[0] = v * jb.scale;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Gradient-penalty coefficient.  One warp per interpolate row b:
 //   n_b = sqrt(sum_t nsq[t][b]);  c_b = lambda * 2/B * (n_b - 1) / n_b;  g1[b,:] *= c_b
-//   pen[b] = (n_b - 1)^2   (summed later by segment_sum_kernel with scale lambda/B)
+//   pen[b] = (n_b - 1)^2   (summed with scale lambda/B by the sum blocks of the next column-sum launch)
 // ---------------------------------------------------------------------------------------------
 __global__ void gp_coef_kernel(const float* __restrict__ nsq, int ntiles, int tile_stride, int rows,
                                float two_lambda_over_B, float* __restrict__ c, float* __restrict__ pen,
@@ -392,7 +375,8 @@ __global__ void blend_kernel(const float* __restrict__ x, int ldx, const float* 
 // ---------------------------------------------------------------------------------------------
 // Column sums over up to three row segments (bias grads, d w3):
 //   out[n] = sum_seg scale_seg * sum_r X_seg[r, n]
-// Stage 1: grid (ceil(N/32), RC): block (32 cols x 8 row lanes) -> part[rc][n].  Stage 2 sums RC.
+// Stage 1: 1-D grid, job j owns ceil(N_j/32) * RC blocks (32 cols x 8 row lanes each) -> part[rc][n], followed
+// by one block per loss-scalar sum.  Stage 2 sums the RC partials in a fixed order.
 // ---------------------------------------------------------------------------------------------
 struct ColsumSeg {
   const float* ptr;
@@ -409,25 +393,69 @@ struct ColsumJob {
 struct ColsumArgs {
   ColsumJob job[3];       // blockIdx.z selects the job
   int part_stride;        // floats of partial storage per job
+  int njobs;
+  int RC;                 // row chunks per column strip
+  int block0[4];          // first block of each job in the 1-D grid; block0[njobs] = first loss-sum block
+  float* zero_out;        // optional: one float to clear (d b3 = sum(+1/B) + sum(-1/B) = 0)
 };
 
-__global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part) {
+__global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part, SumJobs sums, int nsums) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[8][33];
-  const ColsumJob& jb = a.job[blockIdx.z];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + tx;
-  const int RC = gridDim.y, rc = blockIdx.y;
+  const int lin = blockIdx.x;
+  if (lin >= a.block0[a.njobs]) {
+    // trailing blocks: one loss-scalar sum each, in a fixed order (eight independent accumulators per thread so
+    // that the loads overlap instead of forming one latency chain)
+    {
+      const SumJob jb = sums.job[lin - a.block0[a.njobs]];
+      const int bd = blockDim.x;
+      float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int i = threadIdx.x;
+      for (; i + 7 * bd < jb.n; i += 8 * bd) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a8[u] += jb.ptr[i + u * bd];
+      }
+      for (; i < jb.n; i += bd) a8[0] += jb.ptr[i];
+      float acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (tx == 0) red[0][ty] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float v = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v += red[0][i];
+        jb.out[0] = v * jb.scale;
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  const int j = (lin >= a.block0[1] ? 1 : 0) + (lin >= a.block0[2] ? 1 : 0);
+  const ColsumJob& jb = a.job[j];
+  const int strips = (jb.N + 31) >> 5, local = lin - a.block0[j];
+  const int n = (local % strips) * 32 + tx;
+  const int RC = a.RC, rc = local / strips;
   float acc = 0.0f;
   if (n < jb.N) {
     for (int s = 0; s < jb.nseg; ++s) {
       const ColsumSeg sg = jb.seg[s];
       const int per = (sg.rows + RC - 1) / RC;
       const int r0 = rc * per, r1 = min(r0 + per, sg.rows);
-      float t = 0.0f;
-      for (int r = r0 + ty; r < r1; r += 8) t += sg.ptr[static_cast<size_t>(r) * sg.ld + n];
-      acc += sg.scale * t;
+      // four independent chains: the row loads overlap instead of serialising on their latency
+      const float* col = sg.ptr + n;
+      float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+      int r = r0 + ty;
+      for (; r + 24 < r1; r += 32) {
+        t0 += col[static_cast<size_t>(r) * sg.ld];
+        t1 += col[static_cast<size_t>(r + 8) * sg.ld];
+        t2 += col[static_cast<size_t>(r + 16) * sg.ld];
+        t3 += col[static_cast<size_t>(r + 24) * sg.ld];
+      }
+      for (; r < r1; r += 8) t0 += col[static_cast<size_t>(r) * sg.ld];
+      acc += sg.scale * ((t0 + t1) + (t2 + t3));
     }
   }
   red[ty][tx] = acc;
@@ -436,7 +464,7 @@ __global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part) {
     float t = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][tx];
-    part[static_cast<size_t>(blockIdx.z) * a.part_stride + static_cast<size_t>(rc) * jb.N + n] = t;
+    part[static_cast<size_t>(j) * a.part_stride + static_cast<size_t>(rc) * jb.N + n] = t;
   }
 }
 
@@ -445,10 +473,19 @@ __global__ void colsum_final_kernel(ColsumArgs a, const float* __restrict__ part
   pdl_wait();
   const ColsumJob& jb = a.job[blockIdx.y];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a.zero_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.zero_out[0] = 0.0f;
   if (n >= jb.N) return;
-  float t = 0.0f;
-  for (int r = 0; r < RC; ++r) t += part[static_cast<size_t>(blockIdx.y) * a.part_stride + static_cast<size_t>(r) * jb.N + n];
-  jb.out[n] = t;
+  const float* mine = part + static_cast<size_t>(blockIdx.y) * a.part_stride + n;
+  float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;       // four independent chains: the partial loads overlap
+  int r = 0;
+  for (; r + 4 <= RC; r += 4) {
+    t0 += mine[static_cast<size_t>(r) * jb.N];
+    t1 += mine[static_cast<size_t>(r + 1) * jb.N];
+    t2 += mine[static_cast<size_t>(r + 2) * jb.N];
+    t3 += mine[static_cast<size_t>(r + 3) * jb.N];
+  }
+  for (; r < RC; ++r) t0 += mine[static_cast<size_t>(r) * jb.N];
+  jb.out[n] = (t0 + t1) + (t2 + t3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -597,6 +634,63 @@ __global__ void gather_rows_kernel(const float* __restrict__ data, int ldd, cons
     const int64_t src = idx[r];
     *reinterpret_cast<float4*>(out + static_cast<size_t>(r) * ldo + c) =
         *reinterpret_cast<const float4*>(data + static_cast<size_t>(src) * ldd + c);
+  }
+}
+
+// One launch for everything a critic update draws [W:188-193]: block-per-row, row r of the minibatch gets
+//   idx_r = uniform index (Philox stream 3)        -> x_out[r,:] = data[idx_r,:]   (and idx_out[r] if wanted)
+//   z_out[r,:] = noise prior (stream 1),  eps_out[r] = U[0,1) (stream 2, optional)
+// Same counters as the three separate RNG kernels + gather_rows_kernel, so the values are bit-identical.
+__global__ void __launch_bounds__(256)
+draw_minibatch_kernel(const float* __restrict__ data, int ldd, uint32_t n_cells, float* __restrict__ x_out, int ldo,
+                      int cols4, float* __restrict__ z_out, int ldz, int dim, float sigma,
+                      float* __restrict__ eps_out, int64_t* __restrict__ idx_out, long row0, int rows,
+                      uint64_t seed, uint32_t call_id, const uint32_t* __restrict__ call_id_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (call_id_dev != nullptr) call_id += *call_id_dev;
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const uint64_t gr = static_cast<uint64_t>(row0 + r);
+    const uint32_t glo = static_cast<uint32_t>(gr), ghi = static_cast<uint32_t>(gr >> 32);
+    const uint4 ri = philox4x32_10(make_uint4(glo, ghi, call_id, 3u), key);            // block-uniform
+    const int64_t src = static_cast<int64_t>((static_cast<uint64_t>(ri.x) * n_cells) >> 32);
+    const float4* from = reinterpret_cast<const float4*>(data + static_cast<size_t>(src) * ldd);
+    float4* to = reinterpret_cast<float4*>(x_out + static_cast<size_t>(r) * ldo);
+    for (int c = threadIdx.x; c < cols4; c += blockDim.x) to[c] = from[c];
+    if (threadIdx.x == 0) {
+      if (idx_out != nullptr) idx_out[r] = src;
+      if (eps_out != nullptr) {
+        const uint4 re = philox4x32_10(make_uint4(glo, ghi, call_id, 2u), key);
+        eps_out[r] = __fmul_rn(static_cast<float>(re.x >> 8), 5.9604644775390625e-8f);
+      }
+    }
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+      const uint64_t idx = gr * static_cast<uint64_t>(dim) + c;
+      const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), call_id, 1u), key);
+      const float u1 = __fmul_rn(__fadd_rn(static_cast<float>(rnd.x >> 8), 0.5f), 5.9604644775390625e-8f);
+      const float u2 = __fmul_rn(__fadd_rn(static_cast<float>(rnd.y >> 8), 0.5f), 5.9604644775390625e-8f);
+      const float u3 = __fmul_rn(static_cast<float>(rnd.z >> 8), 5.9604644775390625e-8f);
+      const float normal = __fmul_rn(sqrtf(__fmul_rn(-2.0f, logf(u1))), cosf(__fmul_rn(6.2831854820251465f, u2)));
+      float pois = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) pois += (u3 >= c_poisson1_cdf[k]) ? 1.0f : 0.0f;
+      z_out[static_cast<size_t>(r) * ldz + c] = fabsf(__fadd_rn(__fmul_rn(sigma, normal), pois));
+    }
+  }
+}
+
+// Strided 2-D copy (any alignment): dst[r, c] = src[r, c].  Used instead of a memcpy node where the copy sits
+// between two kernels of a step, so that the programmatic-launch chain is not broken.
+__global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows,
+                              int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t total = static_cast<size_t>(rows) * cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+    dst[static_cast<size_t>(r) * ldd + c] = src[static_cast<size_t>(r) * lds + c];
   }
 }
 

@@ -10,6 +10,7 @@ memory, streams and ``torch.distributed``.  There is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import dataclasses
 from typing import Dict, Optional
 
@@ -383,26 +384,42 @@ class WGANTrainer:
             raise _lib.WganError("gather_rows: " + self.lib.wgan_last_error(None).decode())
         return out
 
+    def draw_minibatch(self, batch: int, seed: int, call_id: int, counter=None, data_max_value: float = 1.0):
+        """Indices [W:188] + gather [W:189-191] + noise [W:193] + epsilon of one critic update in a single
+        launch; the same values as indices() / gather() / noise_prior() / uniform() with this call id."""
+        dev = f"cuda:{self.device}"
+        x = self.real_slot(batch)
+        z = torch.empty((batch, self.cfg.noise_input_size), device=dev, dtype=torch.float32)
+        eps = torch.empty((batch,), device=dev, dtype=torch.float32) if self.cfg.lambda_gp != 0 else None
+        rc = self.lib.wgan_draw_minibatch(
+            C.c_void_p(self._data.data_ptr()), self.Gl, self._data.shape[0], C.c_void_p(x.data_ptr()), self.Gl,
+            self.cfg.gex_size, C.c_void_p(z.data_ptr()), z.shape[1], z.shape[1], data_max_value / 10.0,
+            C.c_void_p(eps.data_ptr()) if eps is not None else C.c_void_p(), C.c_void_p(), self.rank * batch, batch,
+            seed, call_id, self._cptr(counter), _stream())
+        if rc != 0:
+            raise _lib.WganError("draw_minibatch: " + self.lib.wgan_last_error(None).decode())
+        return x, z, eps
+
     def train_iteration_resident(self, it: int, batch: int, seed: int = 0, read: bool = False, counter=None):
         """One WGAN-GP iteration with everything drawn on the device: n_critic critic updates
         (fresh minibatch, noise and epsilon each) and one generator update (canonical order),
         or the reference-literal order when cfg.step_order == 'gen_first'.  RNG call ids are
         it * (n_critic + 1) + k; with `counter` (a device uint32) the base comes from the device."""
         cfg = self.cfg
-        n = self._data.shape[0]
         base = 0 if counter is not None else it * (cfg.n_critic + 1)
         out = {}
         if cfg.step_order == "gen_first":
-            z = self.noise_prior(batch, seed=seed, call_id=base, counter=counter)
-            x = self.gather(self.indices(batch, n, seed, base, counter=counter))
-            eps = self.uniform(batch, seed, base, counter=counter) if cfg.lambda_gp != 0 else None
+            x, z, eps = self.draw_minibatch(batch, seed, base, counter=counter)
             return self.train_iteration(x, z, eps, read=read)
+
         def draw(k):
-            cid = base + k
-            z = self.noise_prior(batch, seed=seed, call_id=cid, counter=counter)
-            x = self.gather(self.indices(batch, n, seed, cid, counter=counter))
-            eps = self.uniform(batch, seed, cid, counter=counter) if cfg.lambda_gp != 0 else None
-            return x, z, eps
+            if os.environ.get("WGAN_B200_SPLIT_DRAW"):          # experiment: the four separate launches
+                cid = base + k
+                z = self.noise_prior(batch, seed=seed, call_id=cid, counter=counter)
+                x = self.gather(self.indices(batch, self._data.shape[0], seed, cid, counter=counter))
+                eps = self.uniform(batch, seed, cid, counter=counter) if cfg.lambda_gp != 0 else None
+                return x, z, eps
+            return self.draw_minibatch(batch, seed, base + k, counter=counter)
 
         nxt = draw(0)
         for k in range(cfg.n_critic):

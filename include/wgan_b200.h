@@ -141,6 +141,16 @@ int wgan_counter_add(uint32_t* counter_dev, uint32_t inc, wgan_stream_t stream);
 int wgan_gather_rows(const float* data_dev, int ld_data, const int64_t* idx_dev, float* out_dev,
                      int ld_out, int rows, int cols, wgan_stream_t stream);
 
+/* Everything one critic update draws, in ONE launch (replaces [W:188-193] per update): for minibatch row r
+ * (global row row0 + r) x_out[r,:] = data[idx_r,:] with idx_r the wgan_rng_indices draw, z_out[r,:] the
+ * wgan_rng_noise_prior draw and eps_out[r] the wgan_rng_uniform draw of the same (seed, call id) -- bit-identical
+ * to calling those three and wgan_gather_rows.  eps_out_dev and idx_out_dev may be NULL.  x_out_dev is normally
+ * the real-cell slot of the stacked activation buffer (wgan_get_buffer "xcat"). */
+int wgan_draw_minibatch(const float* data_dev, int ld_data, uint32_t n_cells, float* x_out_dev, int ld_out, int cols,
+                        float* z_out_dev, int ldz, int dim, float sigma, float* eps_out_dev, int64_t* idx_out_dev,
+                        int64_t row0, int rows, uint64_t seed, uint32_t call_id, const uint32_t* call_id_dev,
+                        wgan_stream_t stream);
+
 /* ---- introspection / test hooks ---- */
 /* D[M,N] = epi(A * B^T-ish): a_mn / b_mn select MN-major operands (see csrc/gemm_sm100.cuh).
  * act: 0 none, 1 LeakyReLU(alpha).  Any of bias/aux/row_scale/row_sumsq may be NULL.

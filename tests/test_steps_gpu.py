@@ -233,6 +233,15 @@ def test_resident_data_gather_and_iteration():
     idx = tr.indices(32, 300, seed=5, call_id=0)
     got = tr.gather(idx)
     assert torch.equal(got, data[idx])
+    # the fused draw (one launch) gives exactly the values of the four separate calls
+    ref_x = data[tr.indices(32, 300, seed=5, call_id=7)]
+    ref_z = tr.noise_prior(32, seed=5, call_id=7)
+    ref_e = tr.uniform(32, seed=5, call_id=7)
+    x1, z1, e1 = tr.draw_minibatch(32, seed=5, call_id=7)
+    assert torch.equal(x1, ref_x) and torch.equal(z1, ref_z) and torch.equal(e1, ref_e)
+    cnt = torch.full((1,), 4, dtype=torch.int32, device="cuda:0")
+    x2, z2, e2 = tr.draw_minibatch(32, seed=5, call_id=3, counter=cnt)
+    assert torch.equal(x2, ref_x) and torch.equal(z2, ref_z) and torch.equal(e2, ref_e)
     before = tr.get_tensor("discriminator/disc_dense1/kernel").copy()
     out = tr.train_iteration_resident(0, 32, seed=5, read=True)
     assert set(out) >= {"wasserstein", "gp", "critic_loss", "gen_loss"}
