@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir, mode):
+def _worker(rank, world, port, out_dir, mode, form):
     import torch.distributed as dist
     from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer, PARAM_NAMES
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -28,7 +28,7 @@ def _worker(rank, world, port, out_dir, mode):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     B = 64
-    cfg = WGANConfig(lambda_gp=10.0, learn_rate=1e-3, **DIMS)
+    cfg = WGANConfig(lambda_gp=10.0, learn_rate=1e-3, gp_form=form, **DIMS)
     tr = WGANTrainer(cfg, max_batch=B, device=rank, gemm_mode=mode)
     tr.init_params(seed=4)
     g = np.random.default_rng(0)
@@ -44,16 +44,17 @@ def _worker(rank, world, port, out_dir, mode):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("form", ["explicit", "gram"])
 @pytest.mark.parametrize("mode", [1, 0])
-def test_two_gpu_nccl_matches_single_gpu(tmp_path, mode):
+def test_two_gpu_nccl_matches_single_gpu(tmp_path, mode, form):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from arshamg_scrnaseq_wgan_b200 import WGANConfig, WGANTrainer, PARAM_NAMES
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), mode), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), mode, form), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     B = 64
-    cfg = WGANConfig(lambda_gp=10.0, learn_rate=1e-3, **DIMS)
+    cfg = WGANConfig(lambda_gp=10.0, learn_rate=1e-3, gp_form=form, **DIMS)
     tr = WGANTrainer(cfg, max_batch=B, device=0, gemm_mode=mode, distributed=False)
     tr.init_params(seed=4)
     g = np.random.default_rng(0)
@@ -69,4 +70,5 @@ def test_two_gpu_nccl_matches_single_gpu(tmp_path, mode):
         kk = k.replace("/", "__")
         assert np.array_equal(r0[kk], r1[kk]), k                                  # replicas identical
         ref = tr.get_tensor(k)
-        assert np.linalg.norm(r0[kk] - ref) <= tol * np.linalg.norm(ref) + 1e-7, k
+        # absolute floor: TF-Adam turns summation-order noise in a near-zero gradient entry into a fraction of an lr step
+        assert np.linalg.norm(r0[kk] - ref) <= tol * np.linalg.norm(ref) + 5e-6, k
