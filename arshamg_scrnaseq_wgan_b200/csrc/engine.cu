@@ -403,6 +403,17 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   static const int bn_cap = getenv("WGAN_B200_GEMM_BN") ? atoi(getenv("WGAN_B200_GEMM_BN")) : 0;          // experiments
   int bn = two_cta ? pick_bn_2cta(N, b_mn) : pick_bn(N);
   if (!two_cta && bn_cap >= 32 && bn_cap % 32 == 0 && bn > bn_cap) bn = bn_cap;
+  // latency-bound outputs (the pair tiles would cover less than half of the SMs): halve the tile width, which
+  // halves both the MMA time per K block and the epilogue of the single tile each CTA pair owns
+  static const bool narrow_small = getenv("WGAN_B200_NO_NARROW_SMALL") == nullptr;
+  int kmax = 0;
+  for (int i = 0; i < nparts; ++i) kmax = parts[i].K > kmax ? parts[i].K : kmax;
+  // (not for long reductions over many rows: a second N tile would stream the A operand twice)
+  if (narrow_small && two_cta && N > 128 && N <= bn && (kmax < 1024 || M <= 2 * BM) &&
+      cdiv(M, 2 * BM) * cdiv(N, bn) * nparts * 2 <= h->num_sms / 2) {
+    const int step = b_mn ? 64 : 32;
+    bn = cdiv(cdiv(N, 2), step) * step;
+  }
   const int n_tiles = cdiv(N, bn);
   int msub = 1;
   if (!two_cta && h->gemm_msub == 2 && M >= 2 * BM) msub = 2;   // opt-in: measured slower on every WGAN shape
@@ -579,7 +590,7 @@ int colsum_jobs(wgan_handle* h, const ColsumJob* jobs, int njobs, cudaStream_t s
   a.njobs = njobs;
   a.RC = RC;
   a.zero_out = zero_out;
-  for (int j = 0; j < 3; ++j) a.block0[j + 1] = a.block0[j] + (j < njobs ? cdiv(jobs[j].N, 32) * RC : 0);
+  for (int j = 0; j < 3; ++j) a.block0[j + 1] = a.block0[j] + (j < njobs ? cdiv(jobs[j].N, 128) * RC : 0);
   SumJobs sj;
   memset(&sj, 0, sizeof sj);
   for (int j = 0; j < nsums; ++j) sj.job[j] = sums[j];
@@ -1146,23 +1157,29 @@ int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, 
   const float* Wg3 = h->P(T_WG3); const int ldg3 = h->td[T_WG3].ld;
   const float* Wg2 = h->P(T_WG2); const int ldg2 = h->td[T_WG2].ld;
   TRY(gemm1(h, true, true, h->gh2, Hgl, d3, Gl, h->Gr(T_WG3), ldg3, Hg, G, Bl, epi_none(), s));
+  {
+    // output-bias gradient now, while d3 (108 MB at batch 4096) is still partly L2-resident
+    ColsumJob jb;
+    memset(&jb, 0, sizeof jb);
+    jb.seg[0] = ColsumSeg{d3, Bl, Gl, 1.0f};
+    jb.nseg = 1; jb.N = G; jb.out = h->Gr(T_BG3);
+    TRY(colsum_jobs(h, &jb, 1, s));
+  }
   TRY(gemm1(h, false, false, d3, Gl, Wg3, ldg3, h->gd2, Hgl, Bl, Hg, G, epi_mask(h->gh2, Hgl, a), s));
   TRY(gemm1(h, true, true, h->gh1, Hgl, h->gd2, Hgl, h->Gr(T_WG2), ldg2, Hg, Hg, Bl, epi_none(), s));
   TRY(gemm1(h, false, false, h->gd2, Hgl, Wg2, ldg2, h->gd1, Hgl, Bl, Hg, Hg, epi_mask(h->gh1, Hgl, a), s));
   TRY(gemm1(h, true, true, z, lz, h->gd1, Hgl, h->Gr(T_WG1), h->td[T_WG1].ld, h->Z, Hg, Bl, epi_none(), s));
   {
-    // the three bias gradients (column sums of the layer deltas) in one launch
-    ColsumJob jobs[3];
+    // the two hidden-layer bias gradients and the loss scalar in one launch
+    ColsumJob jobs[2];
     memset(jobs, 0, sizeof jobs);
-    jobs[0].seg[0] = ColsumSeg{d3, Bl, Gl, 1.0f};
-    jobs[0].nseg = 1; jobs[0].N = G; jobs[0].out = h->Gr(T_BG3);
-    jobs[1].seg[0] = ColsumSeg{h->gd2, Bl, Hgl, 1.0f};
-    jobs[1].nseg = 1; jobs[1].N = Hg; jobs[1].out = h->Gr(T_BG2);
-    jobs[2].seg[0] = ColsumSeg{h->gd1, Bl, Hgl, 1.0f};
-    jobs[2].nseg = 1; jobs[2].N = Hg; jobs[2].out = h->Gr(T_BG1);
+    jobs[0].seg[0] = ColsumSeg{h->gd2, Bl, Hgl, 1.0f};
+    jobs[0].nseg = 1; jobs[0].N = Hg; jobs[0].out = h->Gr(T_BG2);
+    jobs[1].seg[0] = ColsumSeg{h->gd1, Bl, Hgl, 1.0f};
+    jobs[1].nseg = 1; jobs[1].N = Hg; jobs[1].out = h->Gr(T_BG1);
     float* sc = h->scalars(WGAN_NET_GENERATOR);
     const SumJob gj = {h->dout, sc + WGAN_S_DFAKE, Bl, invB};          // mean D(G(z)) for obj_g [W:138]
-    TRY(colsum_jobs(h, jobs, 3, s, nullptr, &gj, 1));
+    TRY(colsum_jobs(h, jobs, 2, s, nullptr, &gj, 1));
   }
   return 0;
 }

@@ -375,7 +375,7 @@ __global__ void blend_kernel(const float* __restrict__ x, int ldx, const float* 
 // ---------------------------------------------------------------------------------------------
 // Column sums over up to three row segments (bias grads, d w3):
 //   out[n] = sum_seg scale_seg * sum_r X_seg[r, n]
-// Stage 1: 1-D grid, job j owns ceil(N_j/32) * RC blocks (32 cols x 8 row lanes each) -> part[rc][n], followed
+// Stage 1: 1-D grid, job j owns ceil(N_j/128) * RC blocks (32 float4 columns x 8 row lanes each) -> part[rc][n], followed
 // by one block per loss-scalar sum.  Stage 2 sums the RC partials in a fixed order.
 // ---------------------------------------------------------------------------------------------
 struct ColsumSeg {
@@ -403,6 +403,7 @@ __global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part, Su
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[8][33];
+  __shared__ float4 red4[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int lin = blockIdx.x;
   if (lin >= a.block0[a.njobs]) {
@@ -435,10 +436,10 @@ __global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part, Su
   }
   const int j = (lin >= a.block0[1] ? 1 : 0) + (lin >= a.block0[2] ? 1 : 0);
   const ColsumJob& jb = a.job[j];
-  const int strips = (jb.N + 31) >> 5, local = lin - a.block0[j];
-  const int n = (local % strips) * 32 + tx;
+  const int strips = (jb.N + 127) >> 7, local = lin - a.block0[j];
+  const int n = (local % strips) * 128 + tx * 4;          // this thread's 4 columns (rows are 16 B aligned)
   const int RC = a.RC, rc = local / strips;
-  float acc = 0.0f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (n < jb.N) {
     for (int s = 0; s < jb.nseg; ++s) {
       const ColsumSeg sg = jb.seg[s];
@@ -446,25 +447,41 @@ __global__ void colsum_partial_kernel(ColsumArgs a, float* __restrict__ part, Su
       const int r0 = rc * per, r1 = min(r0 + per, sg.rows);
       // four independent chains: the row loads overlap instead of serialising on their latency
       const float* col = sg.ptr + n;
-      float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       int r = r0 + ty;
       for (; r + 24 < r1; r += 32) {
-        t0 += col[static_cast<size_t>(r) * sg.ld];
-        t1 += col[static_cast<size_t>(r + 8) * sg.ld];
-        t2 += col[static_cast<size_t>(r + 16) * sg.ld];
-        t3 += col[static_cast<size_t>(r + 24) * sg.ld];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 v = *reinterpret_cast<const float4*>(col + static_cast<size_t>(r + 8 * u) * sg.ld);
+          t[u].x += v.x; t[u].y += v.y; t[u].z += v.z; t[u].w += v.w;
+        }
       }
-      for (; r < r1; r += 8) t0 += col[static_cast<size_t>(r) * sg.ld];
-      acc += sg.scale * ((t0 + t1) + (t2 + t3));
+      for (; r < r1; r += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(col + static_cast<size_t>(r) * sg.ld);
+        t[0].x += v.x; t[0].y += v.y; t[0].z += v.z; t[0].w += v.w;
+      }
+      acc.x += sg.scale * ((t[0].x + t[1].x) + (t[2].x + t[3].x));
+      acc.y += sg.scale * ((t[0].y + t[1].y) + (t[2].y + t[3].y));
+      acc.z += sg.scale * ((t[0].z + t[1].z) + (t[2].z + t[3].z));
+      acc.w += sg.scale * ((t[0].w + t[1].w) + (t[2].w + t[3].w));
     }
   }
-  red[ty][tx] = acc;
+  red4[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && n < jb.N) {
-    float t = 0.0f;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][tx];
-    part[static_cast<size_t>(j) * a.part_stride + static_cast<size_t>(rc) * jb.N + n] = t;
+    for (int i = 0; i < 8; ++i) {
+      const float4 v = red4[i][tx];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float* dst = part + static_cast<size_t>(j) * a.part_stride + static_cast<size_t>(rc) * jb.N + n;
+    const float o[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (n + c < jb.N) dst[c] = o[c];
   }
 }
 
