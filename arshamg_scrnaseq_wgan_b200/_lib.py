@@ -75,7 +75,7 @@ SIGNATURES = {
 def build(verbose: bool = False) -> str:
     """Compile csrc/engine.cu into libwgan_b200.so for sm_100a (cross-compiles without a GPU)."""
     src = os.path.join(CSRC_DIR, "engine.cu")
-    deps = [src] + [os.path.join(CSRC_DIR, f) for f in ("gemm_sm100.cuh", "kernels.cuh")] + \
+    deps = [src] + [os.path.join(CSRC_DIR, f) for f in ("gemm_sm100.cuh", "kernels.cuh", "mid_chain_sm100.cuh")] + \
            [os.path.join(INCLUDE_DIR, "wgan_b200.h")]
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH

@@ -22,6 +22,7 @@
 #include "../../include/wgan_b200.h"
 #include "gemm_sm100.cuh"
 #include "kernels.cuh"
+#include "mid_chain_sm100.cuh"
 
 using namespace wg;
 
@@ -72,6 +73,7 @@ struct wgan_handle {
   // workspace
   float *zbuf, *gh1, *gh2, *xcat, *h1, *h2, *d2, *d1, *dout, *v2, *gd2, *gd1, *dz;
   float *nsq, *crow, *pen, *norms, *colpart, *splitws, *sample_tmp;
+  uint32_t *bits1, *bits2;           // [3R][8] slope bits of h1 / h2 (mid_chain_sm100.cuh)
   float *gram_k, *gram_s, *gram_t;   // Gram form of the penalty: W1^T W1, (c g1)^T g1 [Hd, Hd]; g1 K [R, Hd]
   int colpart_stride;
   size_t splitws_n;
@@ -569,6 +571,71 @@ int gemm1(wgan_handle* h, bool a_mn, bool b_mn, const float* A, int lda, const f
   return run_gemm(h, a_mn, b_mn, &p, 1, D, ldd, M, N, e, sumsq_tiles, 0, s);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row-local fused chains (mid_chain_sm100.cuh).  Available on the tensor-core path when the critic's hidden
+// width fits one N tile (H <= 256, H % 8 == 0); otherwise the callers use the separate GEMMs + kernels.
+// ---------------------------------------------------------------------------------------------
+bool mid_chain_available(const wgan_handle* h) {
+  static const bool off = getenv("WGAN_B200_NO_MID_FUSE") != nullptr;
+  return !off && h->cfg.gemm_mode == 0 && h->Hd <= 256 && (h->Hd % 8) == 0;
+}
+
+// `x` carries the mode's scalar / pointer fields; this fills the tensor maps and the geometry.
+int run_mid_chain(wgan_handle* h, int mode, int rows, const float* A, const float* B1, int ldb1, const float* B2,
+                  int ldb2, float* o1, float* o2, float* o3, MidParams x, cudaStream_t s) {
+  const int H = h->Hd, ld = h->Hdl;
+  const int bn = cdiv(H, 32) * 32, KB = cdiv(H, 32);
+  const size_t b_bytes = static_cast<size_t>(bn) * 128, a_bytes = static_cast<size_t>(KB) * 16384;
+  const size_t fixed = 1024 + 2048 + 2048 + 256;       // alignment slack, b2 | w3 vectors, row partials, barriers
+  int stages = static_cast<int>((232448 - fixed - a_bytes) / b_bytes);
+  if (stages > MID_MAX_STAGES) stages = MID_MAX_STAGES;
+  if (stages < 2) FAIL("mid chain: hidden width %d does not fit", H);
+  const size_t smem = fixed + a_bytes + stages * b_bytes;
+  TRY(make_map_2d(h, &x.tma_a, A, H, rows, ld, 32, BM, false));
+  TRY(make_map_mn3d(h, &x.tma_b1, B1, H, H, ldb1, bn / 32));
+  if (mode == 0) TRY(make_map_2d(h, &x.tma_b2, B2, H, H, ldb2, 32, bn, false));
+  else           TRY(make_map_mn3d(h, &x.tma_b2, B2, H, H, ldb2, bn / 32));
+  const size_t slab = round64(static_cast<size_t>(rows) * ld);
+  x.o1 = o1;
+  TRY(make_map_out(h, &x.tma_o2, o2, H, rows, 1, ld, slab));
+  TRY(make_map_out(h, &x.tma_o3, o3, H, rows, 1, ld, slab));
+  x.rows = rows; x.H = H; x.bn = bn; x.kblocks = KB; x.stages = stages;
+  x.alpha = h->cfg.alpha;
+  x.ld = ld;
+  static bool attr_set[16][2] = {};
+  const int dev = h->cfg.device & 15;
+  if (!attr_set[dev][mode]) {
+    if (mode == 0) CK(cudaFuncSetAttribute(mid_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    else           CK(cudaFuncSetAttribute(mid_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set[dev][mode] = true;
+  }
+  if (mode == 0) KLAUNCH(mid_chain_kernel<0>, cdiv(rows, BM), MID_THREADS, smem, s, x);
+  else           KLAUNCH(mid_chain_kernel<1>, cdiv(rows, BM), MID_THREADS, smem, s, x);
+  return post_launch(h, "mid_chain_kernel");
+}
+
+// Critic layer 2 forward, layer 3 + upstream deltas, layer-2 dgrad on `rows` stacked rows whose coefficient
+// segments are `seg` rows long  [W:113-123,137]: fused chain when available, else GEMM + head kernel + GEMM.
+int critic_middle(wgan_handle* h, int rows, int seg, float c0, float c1, float c2, cudaStream_t s) {
+  const int Hd = h->Hd, Hdl = h->Hdl;
+  const float a = h->cfg.alpha;
+  const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
+  if (mid_chain_available(h)) {
+    MidParams x;
+    memset(&x, 0, sizeof x);
+    x.b2 = h->P(T_B2); x.w3 = h->P(T_W3); x.b3 = h->P(T_B3); x.dout = h->dout;
+    x.seg = seg; x.c0 = c0; x.c1 = c1; x.c2 = c2;
+    x.bits1 = h->bits1; x.bits2 = h->bits2;
+    return run_mid_chain(h, 0, rows, h->h1, W2, ldw2, W2, ldw2, h->h2, h->d2, h->d1, x, s);
+  }
+  TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, rows, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
+  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(rows) * 32, 256, h->num_sms), 256, 0, s,
+      h->h2, Hdl, rows, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, seg, c0, c1, c2, a);
+  TRY(post_launch(h, "critic_head_kernel"));
+  // delta1 / g1 = (delta2 W2^T) . slope(h1)
+  return gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, rows, Hd, Hd, epi_mask(h->h1, Hdl, a), s);
+}
+
 // Up to three column-sum jobs in one launch pair: out_j[n] = sum_seg scale * sum_r X_seg[r, n].  `zero_out`
 // (optional) is one extra float to clear; `sums` (optional) are loss-scalar sums evaluated by extra blocks of the
 // first launch.
@@ -671,6 +738,7 @@ void wgan_destroy(wgan_handle* h) {
                    h->gd1, h->dz, h->nsq, h->crow, h->pen, h->norms, h->colpart, h->splitws, h->sample_tmp,
                    h->gram_k, h->gram_s, h->gram_t};
   for (float* b : bufs) cudaFree(b);
+  cudaFree(h->bits1); cudaFree(h->bits2);
   delete h;
 }
 
@@ -699,6 +767,7 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->zbuf = h->gh1 = h->gh2 = h->xcat = h->h1 = h->h2 = h->d2 = h->d1 = h->dout = h->v2 = h->gd2 = h->gd1 =
       h->dz = h->nsq = h->crow = h->pen = h->norms = h->colpart = h->splitws = h->sample_tmp = nullptr;
   h->gram_k = h->gram_s = h->gram_t = nullptr;
+  h->bits1 = h->bits2 = nullptr;
   auto fail = [&](const std::string& m) { g_create_error = m; wgan_destroy(h); return -1; };
 
   h->Z = cfg->noise_input_size; h->Hg = cfg->inflate_to_size; h->G = cfg->gex_size;
@@ -779,6 +848,10 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   for (auto& a : allocs) {
     if (cudaMalloc(a.p, (a.n + 64) * 4) != cudaSuccess) return fail("cudaMalloc(workspace) failed (max_batch too large?)");
     cudaMemset(*a.p, 0, (a.n + 64) * 4);
+  }
+  for (uint32_t** b : {&h->bits1, &h->bits2}) {
+    if (cudaMalloc(b, 3 * R * 8 * sizeof(uint32_t)) != cudaSuccess) return fail("cudaMalloc(slope bits) failed");
+    cudaMemset(*b, 0, 3 * R * 8 * sizeof(uint32_t));
   }
   h->splitws_n = static_cast<size_t>(3 * h->num_sms + 8) * BM * 256;
   {
@@ -928,22 +1001,26 @@ static int critic_grads_gram(wgan_handle* h, const float* eps_dev, int Bl, int g
             round64(static_cast<size_t>(T2) * Hdl), slabs > 0 ? slabs : 1, h->h1, Hdl, Bl, Hd, h->P(T_B1), eps_dev, a);
     TRY(post_launch(h, "l1_gram_finish_kernel"));
   }
-  // layer 2, layer 3 + upstream deltas (fake +1/B, real -1/B, interpolate g2 = w3 . s2)  [W:113-123,137]
-  TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, T, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
-  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(T) * 32, 256, h->num_sms), 256, 0, s,
-      h->h2, Hdl, T, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, invB, -invB, 1.0f, a);
-  TRY(post_launch(h, "critic_head_kernel"));
-  TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, T, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
+  // layer 2, layer 3 + upstream deltas (fake +1/B, real -1/B, interpolate g2 = w3 . s2), delta1 / g1
+  TRY(critic_middle(h, T, Bl, invB, -invB, 1.0f, s));
 
-  // K = W1^T W1, T = g1 K, per-row norm / coefficient, v1 (over h1_hat), T <- c g1
+  // K = W1^T W1, T = g1 K, per-row norm / coefficient, v1 (over h1_hat), T <- c g1, v2 = (v1 W2) . s2
   TRY(gemm1(h, true, true, W1, ldw1, W1, ldw1, h->gram_k, Hdl, Hd, Hd, G, epi_none(), s));
-  TRY(gemm1(h, false, true, g1, Hdl, h->gram_k, Hdl, h->gram_t, Hdl, Bl, Hd, Hd, epi_none(), s));
   h->last_gx_rows = Bl;
-  KLAUNCH(gp_coef_gram_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s,
-      h->gram_t, g1, h1_hat, Hdl, Bl, Hd, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, a);
-  TRY(post_launch(h, "gp_coef_gram_kernel"));
-  // v2 = (v1 W2) . s2
-  TRY(gemm1(h, false, true, h1_hat, Hdl, W2, ldw2, h->v2, Hdl, Bl, Hd, Hd, epi_mask(h2_hat, Hdl, a), s));
+  if (mid_chain_available(h)) {
+    MidParams x;
+    memset(&x, 0, sizeof x);
+    x.bits1 = h->bits1 + static_cast<size_t>(T2) * 8; x.bits2 = h->bits2 + static_cast<size_t>(T2) * 8;   // interpolate rows
+    x.two_lambda_over_B = 2.0f * h->cfg.lambda_gp * invB;
+    x.crow = h->crow; x.pen = h->pen; x.norms = h->norms;
+    TRY(run_mid_chain(h, 1, Bl, g1, h->gram_k, Hdl, W2, ldw2, h->gram_t, h1_hat, h->v2, x, s));
+  } else {
+    TRY(gemm1(h, false, true, g1, Hdl, h->gram_k, Hdl, h->gram_t, Hdl, Bl, Hd, Hd, epi_none(), s));
+    KLAUNCH(gp_coef_gram_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s,
+        h->gram_t, g1, h1_hat, Hdl, Bl, Hd, 2.0f * h->cfg.lambda_gp * invB, h->crow, h->pen, h->norms, a);
+    TRY(post_launch(h, "gp_coef_gram_kernel"));
+    TRY(gemm1(h, false, true, h1_hat, Hdl, W2, ldw2, h->v2, Hdl, Bl, Hd, Hd, epi_mask(h2_hat, Hdl, a), s));
+  }
   // S = (c g1)^T g1
   TRY(gemm1(h, true, true, h->gram_t, Hdl, g1, Hdl, h->gram_s, Hdl, Hd, Hd, Bl, epi_none(), s));
 
@@ -1026,16 +1103,9 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
     TRY(gemm1(h, false, true, h->xcat, Gl, W1, ldw1, h->h1, Hdl, real0, Hd, G, e1, s));
     TRY(gemm1(h, false, true, x, lx, W1, ldw1, h->h1 + static_cast<size_t>(real0) * Hdl, Hdl, Bl, Hd, G, e1, s));
   }
-  // layer 2  [W:113-117]
+  // layer 2 [W:113-117], layer 3 + upstream deltas [W:119-123,137], delta1 / g1 = (delta2 W2^T) . slope(h1)
   const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
-  TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, T, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
-  // layer 3 + upstream deltas  [W:119-123,137]
-  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(T) * 32, 256, h->num_sms), 256, 0, s,
-      h->h2, Hdl, T, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, invB, gp ? 1.0f : -invB,
-      gp ? -invB : 0.0f, a);
-  TRY(post_launch(h, "critic_head_kernel"));
-  // delta1 / g1 = (delta2 W2^T) . slope(h1)
-  TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, T, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
+  TRY(critic_middle(h, T, Bl, invB, gp ? 1.0f : -invB, gp ? -invB : 0.0f, s));
 
   float* h1_hat = h->h1 + static_cast<size_t>(Bl) * Hdl;
   float* h2_hat = h->h2 + static_cast<size_t>(Bl) * Hdl;
@@ -1144,14 +1214,9 @@ int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, 
   float* xt = h->xcat;
   float* d3 = h->xcat + static_cast<size_t>(Bl) * Gl;
   const float* W1 = h->P(T_W1); const int ldw1 = h->td[T_W1].ld;
-  const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
   TRY(gemm1(h, false, true, xt, Gl, W1, ldw1, h->h1, Hdl, Bl, Hd, G, epi_bias_lrelu(h->P(T_B1), a), s));
-  TRY(gemm1(h, false, true, h->h1, Hdl, W2, ldw2, h->h2, Hdl, Bl, Hd, Hd, epi_bias_lrelu(h->P(T_B2), a), s));
-  KLAUNCH(critic_head_kernel, ew_grid(static_cast<size_t>(Bl) * 32, 256, h->num_sms), 256, 0, s,
-      h->h2, Hdl, Bl, Hd, h->P(T_W3), h->P(T_B3), h->dout, h->d2, Bl, -invB, 0.f, 0.f, a);
-  TRY(post_launch(h, "critic_head_kernel"));
-  // back through the critic to the generated cells
-  TRY(gemm1(h, false, false, h->d2, Hdl, W2, ldw2, h->d1, Hdl, Bl, Hd, Hd, epi_mask(h->h1, Hdl, a), s));
+  // critic layers 2 and 3, then back through layer 2 towards the generated cells
+  TRY(critic_middle(h, Bl, Bl, -invB, 0.f, 0.f, s));
   TRY(gemm1(h, false, false, h->d1, Hdl, W1, ldw1, d3, Gl, Bl, G, Hd, epi_mask(xt, Gl, a), s));
   // generator backward
   const float* Wg3 = h->P(T_WG3); const int ldg3 = h->td[T_WG3].ld;
