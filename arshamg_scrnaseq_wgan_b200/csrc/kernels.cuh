@@ -674,7 +674,15 @@ draw_minibatch_kernel(const float* __restrict__ data, int ldd, uint32_t n_cells,
     const int64_t src = static_cast<int64_t>((static_cast<uint64_t>(ri.x) * n_cells) >> 32);
     const float4* from = reinterpret_cast<const float4*>(data + static_cast<size_t>(src) * ldd);
     float4* to = reinterpret_cast<float4*>(x_out + static_cast<size_t>(r) * ldo);
-    for (int c = threadIdx.x; c < cols4; c += blockDim.x) to[c] = from[c];
+    // four independent 16 B loads in flight per thread before the first store
+    int c = threadIdx.x;
+    const int bd = blockDim.x;
+    for (; c + 3 * bd < cols4; c += 4 * bd) {
+      const float4 v0 = __ldg(from + c), v1 = __ldg(from + c + bd), v2 = __ldg(from + c + 2 * bd),
+                   v3 = __ldg(from + c + 3 * bd);
+      to[c] = v0; to[c + bd] = v1; to[c + 2 * bd] = v2; to[c + 3 * bd] = v3;
+    }
+    for (; c < cols4; c += bd) to[c] = __ldg(from + c);
     if (threadIdx.x == 0) {
       if (idx_out != nullptr) idx_out[r] = src;
       if (eps_out != nullptr) {
