@@ -516,9 +516,10 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     p.msub = msub;
     p.nacc = nacc;
     // operands that stream from HBM are prefetched into L2 a few K blocks ahead of the smem ring
-    static const bool l2_prefetch = getenv("WGAN_B200_L2_PREFETCH") != nullptr;   // measured: no gain, off
-    p.prefetch_a = (l2_prefetch && static_cast<size_t>(M) * pt.K * 4 > (8u << 20)) ? 1 : 0;
-    p.prefetch_b = (l2_prefetch && static_cast<size_t>(N) * pt.K * 4 > (8u << 20)) ? 1 : 0;
+    static const int l2_prefetch_mb = getenv("WGAN_B200_L2_PREFETCH") ? atoi(getenv("WGAN_B200_L2_PREFETCH")) : 0;
+    const size_t pf_min = static_cast<size_t>(l2_prefetch_mb) << 20;      // operands at least this large are prefetched
+    p.prefetch_a = (l2_prefetch_mb > 0 && static_cast<size_t>(M) * pt.K * 4 >= pf_min) ? 1 : 0;
+    p.prefetch_b = (l2_prefetch_mb > 0 && static_cast<size_t>(N) * pt.K * 4 >= pf_min) ? 1 : 0;
     // partials that go to the workspace stay raw (p.epi is all-zero) even when this part has a
     // single split; finish_splitk_kernel applies the epilogue after summing the slabs
     if (direct && !raw) p.epi = epi;

@@ -822,6 +822,19 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
         const uint32_t sb = sa + a_bytes;
         const int k0 = kb * BK;
         if (elect_one()) {
+          // a streaming operand's HBM latency under load (2-3 us) is more than the 6-stage ring covers at one
+          // stage per 512 MMA cycles: pull its tile into L2 PREFETCH_DIST K blocks ahead, the ring then sees L2 latency
+          const int kp = kb + PREFETCH_DIST;
+          if (kp < kb1) {
+            if (p.prefetch_a) {
+              if (!A_MN) tma_prefetch_2d(&p.tma_a, kp * BK, m0);
+              else       tma_prefetch_3d(&p.tma_a, 0, kp * BK, m0 / 32);
+            }
+            if (p.prefetch_b) {
+              if (!B_MN) tma_prefetch_2d(&p.tma_b, kp * BK, n0);
+              else       tma_prefetch_3d(&p.tma_b, 0, kp * BK, n0 / 32);
+            }
+          }
           if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * stage_bytes);   // both CTAs' bytes
           if (!A_MN) {
             tma_load_2d_2sm(sa, &p.tma_a, fb, k0, m0);                   // box [128 rows][32 k]

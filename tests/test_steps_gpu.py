@@ -620,3 +620,22 @@ def test_gram_form_graph_replay_and_shard_linearity():
     assert rel < 2e-3, rel
     sc = acc[-4:].cpu().numpy()
     assert abs(sc[2] - s_full["gp"]) < 5e-3 * abs(s_full["gp"])
+
+
+@pytest.mark.parametrize("form", ["explicit", "gram"])
+@pytest.mark.parametrize("hd,B", [(8, 40), (64, 130), (256, 300), (104, 1)])
+def test_fused_row_chains_over_hidden_widths(hd, B, form):
+    """csrc/mid_chain_sm100.cuh (layer 2 + head + dgrad, and the Gram penalty chain, as two chained tcgen05 products per
+    128-row block) across its geometry range: one to eight K blocks, ragged row blocks, a single row."""
+    dims = dict(noise_input_size=12, inflate_to_size=24, gex_size=150, disc_internal_size=hd)
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(dims, B, 10.0, 0, gp_form=form)
+    s = tr.critic_step(xd, zd, ed, apply=False)
+    so, go = O.critic_step_grads(P, x, z, eps, ocfg)
+    wtol = W_TOL[0] * max(1.0, 4.0 / math.sqrt(B))         # a mean over very few rows does not average TF32 rounding
+    assert abs(s["wasserstein"] - so["wasserstein"]) <= wtol * _dscale(P, x, z), (s, so)
+    assert abs(s["gp"] - so["gp"]) <= gp_tol(0, B) * abs(so["gp"]), (s, so)
+    _check_grads(tr.get_grads(O.CRITIC_NAMES), go, O.CRITIC_NAMES, 0, B)
+    s2 = tr.generator_step(zd, apply=False)
+    so2, go2 = O.generator_step_grads(P, z, ocfg)
+    assert abs(s2["gen_loss"] - so2["gen_loss"]) <= wtol * (abs(so2["gen_loss"]) + 1e-6)
+    _check_grads(tr.get_grads(O.GEN_NAMES), go2, O.GEN_NAMES, 0, B)
