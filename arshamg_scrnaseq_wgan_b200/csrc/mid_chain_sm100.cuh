@@ -24,7 +24,9 @@
 // stage-2 operand (= second output, TMA store), then the stage-2 result (TMA store).  Measured on the way: 16 B
 // stores / loads scattered over 32 rows per instruction run at ~1 per cycle per SM (7 K cycles per [128, 200]
 // operand), and 4 KB TMA store boxes at ~31 B/clk per SM -- hence the split between the two paths, and slope
-// masks travel as bit arrays instead of being re-read as floats.
+// masks travel as bit arrays instead of being re-read as floats.  The stage-2 operand is rounded to TF32
+// (cvt.rna, what a TMA load of it would do) before it is written, so delta2 / v1 in global memory carry TF32
+// precision; their only other consumers are TF32 products and one bias-gradient column sum.
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -50,6 +52,7 @@ struct MidParams {
   uint32_t* bits1;          // [rows][8] slope bits (h > 0) of h1 / h2 per 32-column chunk: written by MODE 0,
   uint32_t* bits2;          //           read by MODE 1 (its rows are a row range of the same stacked buffers)
   int rows, H, bn, kblocks, stages;
+  int ld;                   // leading dimension of o1
   float alpha;
   // MODE 0
   const float* b2;
@@ -59,7 +62,6 @@ struct MidParams {
   int seg;                  // rows per coefficient segment
   float c0, c1, c2;
   // MODE 1
-  int ld;
   float two_lambda_over_B;
   float* crow;
   float* pen;
