@@ -163,3 +163,43 @@ def test_minmax_scale_genes():
     raw = O.synthetic_ltpm(50, 40, 0)
     s, _, _ = O.minmax_scale_genes(raw)
     assert s.min() == 0 and s.max() == 1 and raw.min() >= 0
+
+
+def test_gram_form_identities_match_the_explicit_chain():
+    """The Gram form the CUDA path offers (gp_form=1; SURVEY 8d shortcuts i + ii) restated in numpy fp64, step by
+    step as csrc/engine.cu::critic_grads_gram evaluates it, against the explicit chain of the oracle: same penalty,
+    same per-sample norms, same parameter gradients (exact in real arithmetic, <= 1e-12 here)."""
+    cfg = O.OracleConfig(noise_input_size=9, inflate_to_size=14, gex_size=37, disc_internal_size=11, lambda_gp=10.0)
+    P = O.random_params(cfg, seed=3)
+    rng = np.random.default_rng(5)
+    B = 23
+    x = rng.random((B, cfg.gex_size))
+    xt = O.generator_forward(P, np.abs(rng.normal(1.0, 0.5, (B, cfg.noise_input_size))))[2]
+    eps = rng.random(B)
+    gp, g, n = O.gradient_penalty(P, x, xt, eps, cfg.lambda_gp)
+
+    W1, b1, W2, b2, w3 = (P[k] for k in O.CRITIC_NAMES[:5])
+    a = 0.2
+    e = eps.reshape(-1, 1)
+    # (i) layer 1 is linear before its activation: blend the pre-activations, x_hat is never formed
+    h1 = O.lrelu(e * (x @ W1) + (1.0 - e) * (xt @ W1) + b1, a)
+    h2 = O.lrelu(h1 @ W2 + b2, a)
+    s1, s2 = O.slope(h1, a), O.slope(h2, a)
+    g2 = np.ones((B, 1)) @ w3.T * s2
+    g1 = (g2 @ W2.T) * s1
+    # (ii) K = W1^T W1: norms, v1 and the direct W1 term without any product over the gene axis per sample
+    K = W1.T @ W1
+    T = g1 @ K
+    n_gram = np.sqrt((T * g1).sum(axis=1))
+    c = cfg.lambda_gp * 2.0 / B * (n_gram - 1.0) / n_gram
+    v1 = c[:, None] * T * s1
+    S = (c[:, None] * g1).T @ g1
+    dW1 = W1 @ S
+    dW2 = v1.T @ g2
+    dw3 = ((v1 @ W2) * s2).sum(axis=0).reshape(-1, 1)
+    gp_gram = cfg.lambda_gp / B * ((n_gram - 1.0) ** 2).sum()
+
+    assert np.allclose(n_gram, n, rtol=1e-12, atol=0)
+    assert abs(gp_gram - gp) <= 1e-12 * abs(gp)
+    for got, key in ((dW1, O.CRITIC_NAMES[0]), (dW2, O.CRITIC_NAMES[2]), (dw3, O.CRITIC_NAMES[4])):
+        assert np.abs(got - g[key]).max() <= 1e-12 * np.abs(g[key]).max(), key
