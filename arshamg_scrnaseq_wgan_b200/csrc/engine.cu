@@ -1417,6 +1417,24 @@ int wgan_draw_minibatch(const float* data_dev, int ld_data, uint32_t n_cells, fl
     return -2;
   }
   if (upload_poisson_cdf_once() != 0) { g_create_error = "draw_minibatch: constant upload failed"; return -1; }
+  // rows move through the bulk-copy engine (two padded rows of shared memory per block) when they fit
+  const uint32_t row_bytes = static_cast<uint32_t>(round4(cols)) * 4u;
+  static const bool no_bulk = getenv("WGAN_B200_NO_BULK_DRAW") != nullptr;
+  if (!no_bulk && 2u * row_bytes <= 160u * 1024u) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(draw_minibatch_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) !=
+          cudaSuccess) { g_create_error = "draw_minibatch: cudaFuncSetAttribute failed"; return -1; }
+      attr_set = true;
+    }
+    const int per_sm = static_cast<int>((200u * 1024u) / (2u * row_bytes + 1024u));
+    const int cap = 148 * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+    const int grid = rows < cap ? rows : cap;
+    KLAUNCH(draw_minibatch_bulk_kernel, grid, 256, 2u * row_bytes, static_cast<cudaStream_t>(stream), data_dev, ld_data,
+            n_cells, x_out_dev, ld_out, row_bytes, z_out_dev, ldz, dim, sigma, eps_out_dev, idx_out_dev,
+            static_cast<long>(row0), rows, seed, call_id, call_id_dev);
+    return rng_launch_check("draw_minibatch_bulk_kernel");
+  }
   const int grid = rows < 148 * 16 ? rows : 148 * 16;
   KLAUNCH(draw_minibatch_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), data_dev, ld_data, n_cells, x_out_dev,
           ld_out, round4(cols) / 4, z_out_dev, ldz, dim, sigma, eps_out_dev, idx_out_dev, static_cast<long>(row0), rows,

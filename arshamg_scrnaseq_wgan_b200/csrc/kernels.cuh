@@ -705,6 +705,69 @@ draw_minibatch_kernel(const float* __restrict__ data, int ldd, uint32_t n_cells,
   }
 }
 
+// Same draw with the row copies done by the bulk-copy engine instead of the load/store units: thread 0 of a block
+// moves whole padded rows global -> shared -> global with cp.async.bulk (two row buffers in flight per block) while
+// the other threads generate the row's noise.  Bit-identical to draw_minibatch_kernel.
+__global__ void __launch_bounds__(256)
+draw_minibatch_bulk_kernel(const float* __restrict__ data, int ldd, uint32_t n_cells, float* __restrict__ x_out, int ldo,
+                           uint32_t row_bytes, float* __restrict__ z_out, int ldz, int dim, float sigma,
+                           float* __restrict__ eps_out, int64_t* __restrict__ idx_out, long row0, int rows,
+                           uint64_t seed, uint32_t call_id, const uint32_t* __restrict__ call_id_dev) {
+  extern __shared__ __align__(128) uint8_t draw_smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  pdl_launch_dependents();
+  const uint32_t buf0 = smem_u32(draw_smem);
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  if (call_id_dev != nullptr) call_id += *call_id_dev;
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  int it = 0;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x, ++it) {
+    const uint64_t gr = static_cast<uint64_t>(row0 + r);
+    const uint32_t glo = static_cast<uint32_t>(gr), ghi = static_cast<uint32_t>(gr >> 32);
+    if (threadIdx.x == 0) {
+      const uint4 ri = philox4x32_10(make_uint4(glo, ghi, call_id, 3u), key);
+      const int64_t src = static_cast<int64_t>((static_cast<uint64_t>(ri.x) * n_cells) >> 32);
+      const int b = it & 1;
+      const uint32_t buf = buf0 + static_cast<uint32_t>(b) * row_bytes, bar = bar0 + 8u * b;
+      // the store that read this buffer two rows ago must be done with it
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      mbar_expect_tx(bar, row_bytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(buf), "l"(data + static_cast<size_t>(src) * ldd), "r"(row_bytes), "r"(bar) : "memory");
+      if (idx_out != nullptr) idx_out[r] = src;
+      if (eps_out != nullptr) {
+        const uint4 re = philox4x32_10(make_uint4(glo, ghi, call_id, 2u), key);
+        eps_out[r] = __fmul_rn(static_cast<float>(re.x >> 8), 5.9604644775390625e-8f);
+      }
+      mbar_wait(bar, static_cast<uint32_t>(it >> 1) & 1u);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(x_out + static_cast<size_t>(r) * ldo), "r"(buf), "r"(row_bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    } else {
+      for (int c = threadIdx.x - 1; c < dim; c += blockDim.x - 1) {
+        const uint64_t idx = gr * static_cast<uint64_t>(dim) + c;
+        const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), call_id, 1u), key);
+        const float u1 = __fmul_rn(__fadd_rn(static_cast<float>(rnd.x >> 8), 0.5f), 5.9604644775390625e-8f);
+        const float u2 = __fmul_rn(__fadd_rn(static_cast<float>(rnd.y >> 8), 0.5f), 5.9604644775390625e-8f);
+        const float u3 = __fmul_rn(static_cast<float>(rnd.z >> 8), 5.9604644775390625e-8f);
+        const float normal = __fmul_rn(sqrtf(__fmul_rn(-2.0f, logf(u1))), cosf(__fmul_rn(6.2831854820251465f, u2)));
+        float pois = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) pois += (u3 >= c_poisson1_cdf[k]) ? 1.0f : 0.0f;
+        z_out[static_cast<size_t>(r) * ldz + c] = fabsf(__fadd_rn(__fmul_rn(sigma, normal), pois));
+      }
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // Strided 2-D copy (any alignment): dst[r, c] = src[r, c].  Used instead of a memcpy node where the copy sits
 // between two kernels of a step, so that the programmatic-launch chain is not broken.
 __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows,
