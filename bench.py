@@ -11,6 +11,11 @@ driver launches one rank per GPU with torchrun; the batch is sharded by rank (we
 global batch = 4096 * N, one NCCL all-reduce of the flat gradient arena per optimizer step) and
 `value` counts batch-4096 iterations completed by the whole job per second.
 
+`value`, `e2e` and `roofline` refer to the explicit gradient-penalty chain (the work the FLOP table of SURVEY 8d
+counts).  The same workload with the penalty evaluated in its Gram form (`WGANConfig(gp_form="gram")`: identical loss
+and gradients in real arithmetic, SURVEY 8d shortcuts) is timed as well and reported SEPARATELY under `gram_form`
+(`--gp-form gram` runs the whole bench in that form instead; `--no-gram` skips the extra measurement).
+
 `--impl reference` times the reference's CPU implementation of the same path: TensorFlow 1.x is
 not installable here, so this is the FP32 torch-CPU restatement of the reference graph
 (oracle/wgan_torch_cpu.py) on all host cores.
