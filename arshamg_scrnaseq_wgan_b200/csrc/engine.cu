@@ -36,6 +36,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
+constexpr int kB200Sms = 148;      // grid sizing of the handle-less input-pipeline kernels (sm_100a only)
 inline int round4(int x) { return (x + 3) & ~3; }
 inline size_t round64(size_t x) { return (x + 63) & ~static_cast<size_t>(63); }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -1359,7 +1360,7 @@ int wgan_rng_noise_prior(float* out_dev, int ld, int64_t row0, int rows, int dim
   if (!out_dev || rows <= 0 || dim <= 0 || ld < dim) { g_create_error = "rng_noise_prior: bad argument"; return -2; }
   if (upload_poisson_cdf_once() != 0) { g_create_error = "rng_noise_prior: constant upload failed"; return -1; }
   const size_t n = static_cast<size_t>(rows) * dim;
-  int grid = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  int grid = static_cast<int>((n + 255) / 256 > kB200Sms * 16 ? kB200Sms * 16 : (n + 255) / 256);
   KLAUNCH(rng_noise_prior_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), out_dev, ld, row0, rows, dim, sigma,
                                                                                seed, call_id, 1u, call_id_dev);
   return rng_launch_check("rng_noise_prior_kernel");
@@ -1397,7 +1398,7 @@ int wgan_gather_rows(const float* data_dev, int ld_data, const int64_t* idx_dev,
   const int cols4 = round4(cols) / 4;
   if (round4(cols) > ld_data || round4(cols) > ld_out) { g_create_error = "gather_rows: ld smaller than padded cols"; return -2; }
   const size_t n = static_cast<size_t>(rows) * cols4;
-  int grid = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  int grid = static_cast<int>((n + 255) / 256 > kB200Sms * 16 ? kB200Sms * 16 : (n + 255) / 256);
   KLAUNCH(gather_rows_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), data_dev, ld_data, idx_dev, out_dev,
                                                                            ld_out, rows, cols4);
   return rng_launch_check("gather_rows_kernel");
@@ -1421,21 +1422,23 @@ int wgan_draw_minibatch(const float* data_dev, int ld_data, uint32_t n_cells, fl
   const uint32_t row_bytes = static_cast<uint32_t>(round4(cols)) * 4u;
   static const bool no_bulk = getenv("WGAN_B200_NO_BULK_DRAW") != nullptr;
   if (!no_bulk && 2u * row_bytes <= 160u * 1024u) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[16] = {};
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
+    if (!attr_set[dev & 15]) {
       if (cudaFuncSetAttribute(draw_minibatch_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) !=
           cudaSuccess) { g_create_error = "draw_minibatch: cudaFuncSetAttribute failed"; return -1; }
-      attr_set = true;
+      attr_set[dev & 15] = true;
     }
     const int per_sm = static_cast<int>((200u * 1024u) / (2u * row_bytes + 1024u));
-    const int cap = 148 * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+    const int cap = kB200Sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
     const int grid = rows < cap ? rows : cap;
     KLAUNCH(draw_minibatch_bulk_kernel, grid, 256, 2u * row_bytes, static_cast<cudaStream_t>(stream), data_dev, ld_data,
             n_cells, x_out_dev, ld_out, row_bytes, z_out_dev, ldz, dim, sigma, eps_out_dev, idx_out_dev,
             static_cast<long>(row0), rows, seed, call_id, call_id_dev);
     return rng_launch_check("draw_minibatch_bulk_kernel");
   }
-  const int grid = rows < 148 * 16 ? rows : 148 * 16;
+  const int grid = rows < kB200Sms * 16 ? rows : kB200Sms * 16;
   KLAUNCH(draw_minibatch_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), data_dev, ld_data, n_cells, x_out_dev,
           ld_out, round4(cols) / 4, z_out_dev, ldz, dim, sigma, eps_out_dev, idx_out_dev, static_cast<long>(row0), rows,
           seed, call_id, call_id_dev);
