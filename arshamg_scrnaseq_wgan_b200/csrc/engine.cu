@@ -83,6 +83,9 @@ struct wgan_handle {
   int gemm_cluster;                  // preferred cluster size of the tensor-core GEMM (1, 2 or 4)
   int gemm_msub;                     // 0 = auto, 1 / 2 = force 128- / 256-row CTA tiles
   int gemm_2cta;                     // 1 = CTA-pair (cta_group::2) kernel
+  int sm_cap;                        // SMs the persistent GEMM grids may occupy (= num_sms, less inside wgan_*_prepare)
+  int prepare_reserve;               // env WGAN_B200_PREPARE_SM_RESERVE: SMs left free for a concurrent collective
+                                     // while the prepare calls run next to a gradient all-reduce (0 = off, default)
   // wgan_critic_prepare ran the parameter-independent-of-the-critic part (input staging, G(z), interpolate)
   // for exactly these arguments; the next wgan_critic_grads with the same arguments skips it
   const float* prep_x; const float* prep_z; const float* prep_eps; int prep_rows;
@@ -318,6 +321,7 @@ int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int cluster_tile
     max_clusters[dev][p.cluster] = n;
   }
   int clusters = cluster_tiles < max_clusters[dev][p.cluster] ? cluster_tiles : max_clusters[dev][p.cluster];
+  if (clusters > h->sm_cap / p.cluster) clusters = h->sm_cap / p.cluster;
   cfg.gridDim = dim3(clusters * p.cluster);
   CK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN>, p));
   return post_launch(h, "gemm_tf32_kernel");
@@ -347,7 +351,7 @@ int launch_tc2(wgan_handle* h, const GemmParams& p, size_t smem, int pair_tiles,
   attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  const int max_pairs = h->num_sms / 2;
+  const int max_pairs = h->sm_cap / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
   cfg.gridDim = dim3(pairs * 2);
   CK(cudaLaunchKernelEx(&cfg, gemm_tf32_2cta_kernel<A_MN, B_MN>, p));
@@ -756,6 +760,8 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->gprep_z = nullptr; h->gprep_rows = 0;
   h->gemm_2cta = 1;
   if (const char* env = getenv("WGAN_B200_GEMM_2CTA")) h->gemm_2cta = atoi(env) != 0;
+  h->prepare_reserve = 0;
+  if (const char* env = getenv("WGAN_B200_PREPARE_SM_RESERVE")) h->prepare_reserve = atoi(env) > 0 ? atoi(env) : 0;
   h->gemm_msub = 0;
   if (const char* env = getenv("WGAN_B200_GEMM_MSUB")) {
     int c = atoi(env);
@@ -787,6 +793,8 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
   if (prop.major != 10) return fail("this library is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
   h->num_sms = prop.multiProcessorCount;
+  h->sm_cap = h->num_sms;
+  if (h->prepare_reserve > h->num_sms / 2) h->prepare_reserve = h->num_sms / 2;
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -1065,7 +1073,10 @@ int wgan_critic_prepare(wgan_handle* h, const float* x_dev, int ldx, const float
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
   if (h->cfg.lambda_gp != 0.0f && !eps_dev) FAIL("critic_prepare: eps required when lambda_gp != 0");
-  TRY(critic_phase_a(h, x_dev, ldx, z_dev, ldz, eps_dev, rows, static_cast<cudaStream_t>(stream)));
+  h->sm_cap = h->num_sms - h->prepare_reserve;
+  const int rc = critic_phase_a(h, x_dev, ldx, z_dev, ldz, eps_dev, rows, static_cast<cudaStream_t>(stream));
+  h->sm_cap = h->num_sms;
+  TRY(rc);
   h->prep_x = x_dev; h->prep_z = z_dev; h->prep_eps = eps_dev; h->prep_rows = rows;
   return 0;
 }
@@ -1194,7 +1205,10 @@ int wgan_generator_prepare(wgan_handle* h, const float* z_dev, int ldz, int rows
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
   h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
-  TRY(generator_phase_a(h, z_dev, ldz, rows, static_cast<cudaStream_t>(stream)));
+  h->sm_cap = h->num_sms - h->prepare_reserve;
+  const int rc = generator_phase_a(h, z_dev, ldz, rows, static_cast<cudaStream_t>(stream));
+  h->sm_cap = h->num_sms;
+  TRY(rc);
   h->gprep_z = z_dev; h->gprep_rows = rows;
   return 0;
 }
