@@ -25,7 +25,7 @@ class WganConfig(C.Structure):
         ("disc_internal_size", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32),
         ("gemm_mode", C.c_int32), ("gp_form", C.c_int32),
         ("learn_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
-        ("alpha", C.c_float), ("lambda_gp", C.c_float), ("reserved1", C.c_float), ("reserved2", C.c_float),
+        ("alpha", C.c_float), ("lambda_gp", C.c_float), ("dp_rank", C.c_int32), ("dp_world", C.c_int32),
     ]
 
 
@@ -48,12 +48,15 @@ SIGNATURES = {
     "wgan_set_adam_powers": (_I, [_P, _I, _F, _F]),
     "wgan_get_arena": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "wgan_get_scalars": (_I, [_P, _I, _P, _P]),
-    "wgan_critic_grads": (_I, [_P, _P, _I, _P, _I, _P, _I, _I, _P]),
-    "wgan_critic_prepare": (_I, [_P, _P, _I, _P, _I, _P, _I, _P]),
+    "wgan_critic_grads": (_I, [_P, _P, _I, _P, _I, _P, _I, _I, C.c_uint64, _P]),
+    "wgan_critic_prepare": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, C.POINTER(C.c_uint64)]),
     "wgan_critic_apply": (_I, [_P, _P]),
-    "wgan_generator_grads": (_I, [_P, _P, _I, _I, _I, _P]),
-    "wgan_generator_prepare": (_I, [_P, _P, _I, _I, _P]),
+    "wgan_generator_grads": (_I, [_P, _P, _I, _I, _I, C.c_uint64, _P]),
+    "wgan_generator_prepare": (_I, [_P, _P, _I, _I, _P, C.POINTER(C.c_uint64)]),
     "wgan_generator_apply": (_I, [_P, _P]),
+    "wgan_dp_export": (_I, [_P, _P]),
+    "wgan_dp_connect": (_I, [_P, _P]),
+    "wgan_allreduce_grads": (_I, [_P, _I, _P]),
     "wgan_sample": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "wgan_critic_forward": (_I, [_P, _P, _I, _P, _I, _P]),
     "wgan_latent_fit_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _F, _P]),
@@ -107,6 +110,10 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+DP_MAX_WORLD = 16          # WGAN_DP_MAX_WORLD
+DP_BLOB_BYTES = 128        # WGAN_DP_BLOB_BYTES
 
 
 class WganError(RuntimeError):

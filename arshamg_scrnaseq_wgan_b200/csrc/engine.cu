@@ -18,6 +18,7 @@
 #include <utility>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 #include "../../include/wgan_b200.h"
 #include "gemm_sm100.cuh"
@@ -86,10 +87,22 @@ struct wgan_handle {
   int sm_cap;                        // SMs the persistent GEMM grids may occupy (= num_sms, less inside wgan_*_prepare)
   int prepare_reserve;               // env WGAN_B200_PREPARE_SM_RESERVE: SMs left free for a concurrent collective
                                      // while the prepare calls run next to a gradient all-reduce (0 = off, default)
-  // wgan_critic_prepare ran the parameter-independent-of-the-critic part (input staging, G(z), interpolate)
-  // for exactly these arguments; the next wgan_critic_grads with the same arguments skips it
-  const float* prep_x; const float* prep_z; const float* prep_eps; int prep_rows;
-  const float* gprep_z; int gprep_rows;   // same for wgan_generator_prepare / wgan_generator_grads
+  // Prepared state.  wgan_critic_prepare / wgan_generator_prepare run the part of a step that does not depend on
+  // the critic's parameters and hand back a token (= the workspace generation they left behind).  Every entry
+  // point that writes the shared activation workspace advances `ws_gen`, so a token is honoured only while the
+  // prepared activations are still intact; a stale token just means the work is redone.
+  uint64_t ws_gen;
+  uint64_t prep_token; int prep_rows;      // critic: token of the last critic_prepare (0 = none)
+  uint64_t gprep_token; int gprep_rows;    // generator
+  unsigned int* sk_flags;                  // stream-K partial-ready flags [pair][cta][epilogue warp] (gemm_sm100.cuh)
+  bool attr_tc[4], attr_tc2[4], attr_mid[2];   // cudaFuncSetAttribute done for this handle's device, per instantiation
+  int max_clusters[4][5];
+  // data-parallel window: both gradient arenas + the cross-GPU flags in ONE allocation that peers map
+  // (cudaIpc handle or, inside one process, the pointer itself); see dp_allreduce_kernel in kernels.cuh
+  float* dp_win; size_t dp_win_bytes; size_t dp_grad_off[2]; size_t dp_flags_off;
+  int dp_rank, dp_world, dp_blocks; bool dp_connected;
+  float* dp_peer[WGAN_DP_MAX_WORLD];       // window base of every rank as mapped here (own rank: dp_win)
+  bool dp_peer_ipc[WGAN_DP_MAX_WORLD];     // opened with cudaIpcOpenMemHandle (closed in wgan_destroy)
 
   float* P(int t) { return arena[td[t].net][WGAN_KIND_PARAM] + td[t].offset; }
   float* Gr(int t) { return arena[td[t].net][WGAN_KIND_GRAD] + td[t].offset; }
@@ -289,13 +302,13 @@ int launch_finish(wgan_handle* h, const float* part, size_t slab, int splits, fl
 // Launches min(cluster_tiles, co-resident clusters) clusters of p.cluster persistent CTAs.
 template <bool A_MN, bool B_MN>
 int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int cluster_tiles, cudaStream_t s) {
-  static bool attr_set[16] = {};
-  static int max_clusters[16][5] = {};
-  int dev = h->cfg.device & 15;
-  if (!attr_set[dev]) {
+  // attribute / occupancy state is per handle (a handle is bound to one device and one host thread)
+  constexpr int inst = (A_MN ? 2 : 0) + (B_MN ? 1 : 0);
+  int* max_clusters = h->max_clusters[inst];
+  if (!h->attr_tc[inst]) {
     CK(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             232448));
-    attr_set[dev] = true;
+    h->attr_tc[inst] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -311,16 +324,16 @@ int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int cluster_tile
   attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  if (max_clusters[dev][p.cluster] == 0) {
+  if (max_clusters[p.cluster] == 0) {
     int n = 0;
     cfg.gridDim = dim3(h->num_sms / p.cluster * p.cluster);
     if (p.cluster == 1 || cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<A_MN, B_MN>, &cfg) != cudaSuccess ||
         n <= 0)
       n = h->num_sms / p.cluster;
     (void)cudaGetLastError();
-    max_clusters[dev][p.cluster] = n;
+    max_clusters[p.cluster] = n;
   }
-  int clusters = cluster_tiles < max_clusters[dev][p.cluster] ? cluster_tiles : max_clusters[dev][p.cluster];
+  int clusters = cluster_tiles < max_clusters[p.cluster] ? cluster_tiles : max_clusters[p.cluster];
   if (clusters > h->sm_cap / p.cluster) clusters = h->sm_cap / p.cluster;
   cfg.gridDim = dim3(clusters * p.cluster);
   CK(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN>, p));
@@ -330,12 +343,11 @@ int launch_tc(wgan_handle* h, const GemmParams& p, size_t smem, int cluster_tile
 // CTA-pair kernel: cluster (2,1,1), at most num_sms/2 co-resident pairs.
 template <bool A_MN, bool B_MN>
 int launch_tc2(wgan_handle* h, const GemmParams& p, size_t smem, int pair_tiles, cudaStream_t s) {
-  static bool attr_set[16] = {};
-  int dev = h->cfg.device & 15;
-  if (!attr_set[dev]) {
+  constexpr int inst = (A_MN ? 2 : 0) + (B_MN ? 1 : 0);
+  if (!h->attr_tc2[inst]) {
     CK(cudaFuncSetAttribute(gemm_tf32_2cta_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             232448));
-    attr_set[dev] = true;
+    h->attr_tc2[inst] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -447,7 +459,9 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   for (int i = 0; i < nparts; ++i) {
     const int total_kb = cdiv(parts[i].K, BK);
     int sp = 1;
-    if (force_splits > 0) {
+    if (force_splits < 0) {
+      sp = 1;
+    } else if (force_splits > 0) {
       sp = force_splits;
     } else {
       // smallest split count whose work units fill >= 85 % of the last wave of persistent CTAs (pairs),
@@ -470,6 +484,22 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     splits[i] = sp;
     kbps[i] = per;
     total_splits += sp;
+  }
+  // Stream-K (CTA-pair kernel): where split-K would be chosen for a single fused product whose tiles are at most
+  // ~4 pairs apiece, every pair instead streams one contiguous range of (tile, K block) units; partial accumulators
+  // meet in the workspace and the tile's owner runs the fused epilogue -- no slabs, no finish pass, no idle pairs.
+  // force_splits < 0 forces it (tests), > 0 forces split-K.
+  static const bool no_sk = getenv("WGAN_B200_NO_STREAMK") != nullptr;
+  const int sk_pairs = h->sm_cap / 2;
+  bool streamk = false;
+  if (!no_sk && two_cta && nparts == 1 && !raw && cdiv(parts[0].K, BK) >= 2 &&
+      ((force_splits == 0 && splits[0] > 1 && tiles * 4 >= sk_pairs) || force_splits < 0) &&
+      static_cast<long long>(tiles) * cdiv(parts[0].K, BK) >= sk_pairs &&
+      static_cast<size_t>(sk_pairs) * 2 * SK_SLOT_FLOATS <= h->splitws_n) {
+    streamk = true;
+    splits[0] = 1;
+    kbps[0] = cdiv(parts[0].K, BK);
+    total_splits = 1;
   }
   if (total_splits > 1 && slab * (ws_slab0 + total_splits) > h->splitws_n) {
     if (nparts > 1) FAIL("gemm: split workspace too small for %d slabs of %zu floats", total_splits, slab);
@@ -529,7 +559,13 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     // single split; finish_splitk_kernel applies the epilogue after summing the slabs
     if (direct && !raw) p.epi = epi;
     else if (!direct) p.splits = splits[i];
-    const int grid = m_groups * n_tiles * splits[i];       // cluster tiles; launch_tc caps at residency
+    if (streamk) {
+      p.streamk = 1;
+      p.sk_units = static_cast<long long>(tiles) * p.total_kb;
+      p.sk_ws = h->splitws;
+      p.sk_flags = h->sk_flags;
+    }
+    const int grid = streamk ? sk_pairs : m_groups * n_tiles * splits[i];   // cluster tiles; launch_tc caps at residency
     if (two_cta) {
       if (!a_mn && b_mn) TRY((launch_tc2<false, true>(h, p, smem, grid, s)));
       else if (!a_mn && !b_mn) TRY((launch_tc2<false, false>(h, p, smem, grid, s)));
@@ -608,12 +644,10 @@ int run_mid_chain(wgan_handle* h, int mode, int rows, const float* A, const floa
   x.rows = rows; x.H = H; x.bn = bn; x.kblocks = KB; x.stages = stages;
   x.alpha = h->cfg.alpha;
   x.ld = ld;
-  static bool attr_set[16][2] = {};
-  const int dev = h->cfg.device & 15;
-  if (!attr_set[dev][mode]) {
+  if (!h->attr_mid[mode]) {
     if (mode == 0) CK(cudaFuncSetAttribute(mid_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     else           CK(cudaFuncSetAttribute(mid_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set[dev][mode] = true;
+    h->attr_mid[mode] = true;
   }
   if (mode == 0) KLAUNCH(mid_chain_kernel<0>, cdiv(rows, BM), MID_THREADS, smem, s, x);
   else           KLAUNCH(mid_chain_kernel<1>, cdiv(rows, BM), MID_THREADS, smem, s, x);
@@ -703,6 +737,9 @@ int generator_forward(wgan_handle* h, const float* z, int ldz, int rows, float* 
   return run_gemm(h, false, true, &p3, 1, xt, ldxt, rows, h->G, e3, nullptr, 0, s, blend_out);
 }
 
+// Every entry point that writes the shared activation workspace calls this first: outstanding prepare tokens die.
+inline void invalidate_workspace(wgan_handle* h) { ++h->ws_gen; }
+
 int check_rows(wgan_handle* h, int rows, int global_batch) {
   if (rows <= 0 || rows > h->R) FAIL("rows=%d outside (0, max_batch=%d]", rows, h->R);
   if (global_batch < rows) FAIL("global_batch=%d < rows=%d", global_batch, rows);
@@ -736,10 +773,15 @@ int64_t wgan_launch_count(const wgan_handle* h) {
 void wgan_destroy(wgan_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  for (int r = 0; r < WGAN_DP_MAX_WORLD; ++r)
+    if (h->dp_peer_ipc[r] && h->dp_peer[r] != nullptr) cudaIpcCloseMemHandle(h->dp_peer[r]);
   for (int n = 0; n < 2; ++n) {
-    for (int k = 0; k < 4; ++k) cudaFree(h->arena[n][k]);
+    for (int k = 0; k < 4; ++k)
+      if (k != WGAN_KIND_GRAD) cudaFree(h->arena[n][k]);      // the gradient arenas live in the DP window
     cudaFree(h->powers[n]);
   }
+  cudaFree(h->dp_win);
+  cudaFree(h->sk_flags);
   float* bufs[] = {h->zbuf, h->gh1, h->gh2, h->xcat, h->h1, h->h2, h->d2, h->d1, h->dout, h->v2, h->gd2,
                    h->gd1, h->dz, h->nsq, h->crow, h->pen, h->norms, h->colpart, h->splitws, h->sample_tmp,
                    h->gram_k, h->gram_s, h->gram_t};
@@ -756,8 +798,20 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->launches = 0;
   h->last_gx_rows = 0;
   h->gemm_cluster = 1;
-  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
-  h->gprep_z = nullptr; h->gprep_rows = 0;
+  h->ws_gen = 0;
+  h->prep_token = h->gprep_token = 0; h->prep_rows = h->gprep_rows = 0;
+  h->sk_flags = nullptr;
+  memset(h->attr_tc, 0, sizeof h->attr_tc); memset(h->attr_tc2, 0, sizeof h->attr_tc2);
+  memset(h->attr_mid, 0, sizeof h->attr_mid); memset(h->max_clusters, 0, sizeof h->max_clusters);
+  h->dp_win = nullptr; h->dp_win_bytes = 0; h->dp_connected = false;
+  h->dp_world = cfg->dp_world > 1 ? cfg->dp_world : 1;
+  h->dp_rank = cfg->dp_world > 1 ? cfg->dp_rank : 0;
+  h->dp_blocks = 32;
+  if (const char* env = getenv("WGAN_B200_DP_BLOCKS")) {
+    const int b = atoi(env);
+    if (b >= 1 && b <= DP_MAX_BLOCKS) h->dp_blocks = b;
+  }
+  for (int r = 0; r < WGAN_DP_MAX_WORLD; ++r) { h->dp_peer[r] = nullptr; h->dp_peer_ipc[r] = false; }
   h->gemm_2cta = 1;
   if (const char* env = getenv("WGAN_B200_GEMM_2CTA")) h->gemm_2cta = atoi(env) != 0;
   h->prepare_reserve = 0;
@@ -783,6 +837,8 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   if (h->Z <= 0 || h->Hg <= 0 || h->G <= 0 || h->Hd <= 0 || h->R <= 0) return fail("non-positive dimension in config");
   if (cfg->gemm_mode != 0 && cfg->gemm_mode != 1) return fail("gemm_mode must be 0 (TF32 tcgen05) or 1 (FP32 verify)");
   if (cfg->gp_form != 0 && cfg->gp_form != 1) return fail("gp_form must be 0 (explicit chain) or 1 (Gram form)");
+  if (cfg->dp_world > WGAN_DP_MAX_WORLD) return fail("dp_world exceeds WGAN_DP_MAX_WORLD");
+  if (cfg->dp_world > 1 && (cfg->dp_rank < 0 || cfg->dp_rank >= cfg->dp_world)) return fail("dp_rank outside [0, dp_world)");
   h->Zl = round4(h->Z); h->Hgl = round4(h->Hg); h->Gl = round4(h->G); h->Hdl = round4(h->Hd);
 
   int ndev = 0;
@@ -831,9 +887,18 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
     d.offset = off[d.net];
     off[d.net] += round64(static_cast<size_t>(d.rows) * d.ld);
   }
+  // both gradient arenas and the data-parallel flags share ONE allocation, the window peers map (wgan_dp_connect)
+  for (int n = 0; n < 2; ++n) h->arena_n[n] = off[n] + 4;
+  h->dp_grad_off[WGAN_NET_CRITIC] = 0;
+  h->dp_grad_off[WGAN_NET_GENERATOR] = round64(h->arena_n[WGAN_NET_CRITIC]);
+  h->dp_flags_off = h->dp_grad_off[WGAN_NET_GENERATOR] + round64(h->arena_n[WGAN_NET_GENERATOR]);
+  h->dp_win_bytes = (h->dp_flags_off + DP_FLAG_WORDS) * 4;
+  if (cudaMalloc(&h->dp_win, h->dp_win_bytes) != cudaSuccess) return fail("cudaMalloc(gradient window) failed");
+  cudaMemset(h->dp_win, 0, h->dp_win_bytes);
+  h->dp_peer[h->dp_rank] = h->dp_win;
   for (int n = 0; n < 2; ++n) {
-    h->arena_n[n] = off[n] + 4;
     for (int k = 0; k < 4; ++k) {
+      if (k == WGAN_KIND_GRAD) { h->arena[n][k] = h->dp_win + h->dp_grad_off[n]; continue; }
       if (cudaMalloc(&h->arena[n][k], h->arena_n[n] * 4) != cudaSuccess) return fail("cudaMalloc(arena) failed");
       cudaMemset(h->arena[n][k], 0, h->arena_n[n] * 4);
     }
@@ -871,6 +936,11 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
     if (h->splitws_n < need) h->splitws_n = need;
   }
   if (cudaMalloc(&h->splitws, h->splitws_n * 4) != cudaSuccess) return fail("cudaMalloc(split workspace) failed");
+  {
+    const size_t nflags = static_cast<size_t>(h->num_sms / 2 + 1) * 2 * NUM_EPI_WARPS;
+    if (cudaMalloc(&h->sk_flags, nflags * 4) != cudaSuccess) return fail("cudaMalloc(stream-K flags) failed");
+    cudaMemset(h->sk_flags, 0, nflags * 4);
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) return fail("device error during create");
   *out = h;
   return 0;
@@ -948,7 +1018,6 @@ int wgan_get_scalars(wgan_handle* h, int net, float* host4, wgan_stream_t stream
 // k+1 while the gradient all-reduce of update k is in flight.
 static int critic_phase_a(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
                           const float* eps_dev, int rows, cudaStream_t s) {
-  h->gprep_z = nullptr; h->gprep_rows = 0;               // shares zbuf / gh1 / gh2 / xcat with the generator step
   const bool gp = h->cfg.lambda_gp != 0.0f;
   const int Bl = rows, nh = gp ? 1 : 0;
   const int G = h->G, Gl = h->Gl;
@@ -956,16 +1025,14 @@ static int critic_phase_a(wgan_handle* h, const float* x_dev, int ldx, const flo
   const int real0 = gram ? Bl : (1 + nh) * Bl;
   const float* z; int lz;
   TRY(stage_input(h, z_dev, ldz, Bl, h->Z, h->zbuf, h->Zl, &z, &lz, s));
+  // the real cells always live in their slot of the stacked buffer (layer 1 and its weight gradient are single
+  // products over the stacked rows, and the weight gradient's column-chunked reads never touch caller memory)
   float* xreal_slot = h->xcat + static_cast<size_t>(real0) * Gl;
-  if (gram) {
-    // Gram form: rows [fake | real] are one stacked operand; x^ is never formed
-    if (x_dev != xreal_slot || ldx != Gl)
-      CK(cudaMemcpy2DAsync(xreal_slot, static_cast<size_t>(Gl) * 4, x_dev, static_cast<size_t>(ldx) * 4,
-                           static_cast<size_t>(G) * 4, Bl, cudaMemcpyDeviceToDevice, s));
-    return generator_forward(h, z, lz, Bl, h->xcat, Gl, s);
-  }
-  const float* x; int lx;
-  TRY(stage_input(h, x_dev, ldx, Bl, G, xreal_slot, Gl, &x, &lx, s));
+  if (x_dev != xreal_slot || ldx != Gl)
+    CK(cudaMemcpy2DAsync(xreal_slot, static_cast<size_t>(Gl) * 4, x_dev, static_cast<size_t>(ldx) * 4,
+                         static_cast<size_t>(G) * 4, Bl, cudaMemcpyDeviceToDevice, s));
+  if (gram) return generator_forward(h, z, lz, Bl, h->xcat, Gl, s);   // rows [fake | real]; x^ is never formed
+  const float* x = xreal_slot; const int lx = Gl;
   float* xt = h->xcat;
   float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;    // interpolates, later overwritten by gx
   // the interpolate x^ = eps x + (1 - eps) x~ is a second output of the generator-output GEMM
@@ -1067,22 +1134,26 @@ static int critic_grads_gram(wgan_handle* h, const float* eps_dev, int Bl, int g
 }
 
 int wgan_critic_prepare(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
-                        const float* eps_dev, int rows, wgan_stream_t stream) {
+                        const float* eps_dev, int rows, wgan_stream_t stream, uint64_t* token_out) {
   if (!h) return -2;
+  if (token_out) *token_out = 0;
   if (!x_dev || !z_dev) FAIL("critic_prepare: null input");
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
   if (h->cfg.lambda_gp != 0.0f && !eps_dev) FAIL("critic_prepare: eps required when lambda_gp != 0");
+  invalidate_workspace(h);
   h->sm_cap = h->num_sms - h->prepare_reserve;
   const int rc = critic_phase_a(h, x_dev, ldx, z_dev, ldz, eps_dev, rows, static_cast<cudaStream_t>(stream));
   h->sm_cap = h->num_sms;
   TRY(rc);
-  h->prep_x = x_dev; h->prep_z = z_dev; h->prep_eps = eps_dev; h->prep_rows = rows;
+  h->prep_token = h->ws_gen; h->prep_rows = rows;
+  if (token_out) *token_out = h->prep_token;
   return 0;
 }
 
 int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
-                      const float* eps_dev, int rows, int global_batch, wgan_stream_t stream) {
+                      const float* eps_dev, int rows, int global_batch, uint64_t prepared_token,
+                      wgan_stream_t stream) {
   if (!h) return -2;
   if (!x_dev || !z_dev) FAIL("critic_grads: null input");
   TRY(check_rows(h, rows, global_batch));
@@ -1095,27 +1166,18 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   const float a = h->cfg.alpha, invB = 1.0f / static_cast<float>(global_batch);
   const int real0 = (1 + nh) * Bl;                       // first real row in the stacked buffers
 
-  const bool prepared = (h->prep_x == x_dev && h->prep_z == z_dev && h->prep_eps == eps_dev && h->prep_rows == rows);
-  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
+  // the prepared activations are still intact iff nothing has touched the workspace since that prepare call
+  const bool prepared = prepared_token != 0 && prepared_token == h->prep_token && prepared_token == h->ws_gen &&
+                        h->prep_rows == rows;
+  invalidate_workspace(h);
   if (!prepared) TRY(critic_phase_a(h, x_dev, ldx, z_dev, ldz, eps_dev, rows, s));
   if (gp && h->cfg.gp_form == 1) return critic_grads_gram(h, eps_dev, rows, global_batch, s);
-  // where phase A left the inputs
-  float* xreal_slot = h->xcat + static_cast<size_t>(real0) * Gl;
-  const bool x_legal = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && (ldx & 3) == 0;
-  const float* x = x_legal ? x_dev : xreal_slot;
-  const int lx = x_legal ? ldx : Gl;
-  const bool x_stacked = (x == xreal_slot && lx == Gl);
   float* xh = h->xcat + static_cast<size_t>(Bl) * Gl;
 
   // critic layer 1 on [fake | hat | real]  [W:107-111]
   const EpiParams e1 = epi_bias_lrelu(h->P(T_B1), a);
   const float* W1 = h->P(T_W1); const int ldw1 = h->td[T_W1].ld;
-  if (x_stacked) {
-    TRY(gemm1(h, false, true, h->xcat, Gl, W1, ldw1, h->h1, Hdl, T, Hd, G, e1, s));
-  } else {
-    TRY(gemm1(h, false, true, h->xcat, Gl, W1, ldw1, h->h1, Hdl, real0, Hd, G, e1, s));
-    TRY(gemm1(h, false, true, x, lx, W1, ldw1, h->h1 + static_cast<size_t>(real0) * Hdl, Hdl, Bl, Hd, G, e1, s));
-  }
+  TRY(gemm1(h, false, true, h->xcat, Gl, W1, ldw1, h->h1, Hdl, T, Hd, G, e1, s));
   // layer 2 [W:113-117], layer 3 + upstream deltas [W:119-123,137], delta1 / g1 = (delta2 W2^T) . slope(h1)
   const float* W2 = h->P(T_W2); const int ldw2 = h->td[T_W2].ld;
   TRY(critic_middle(h, T, Bl, invB, gp ? 1.0f : -invB, gp ? -invB : 0.0f, s));
@@ -1142,19 +1204,7 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
   }
 
   // weight gradients
-  {
-    Part parts[2];
-    int np;
-    if (x_stacked) {
-      parts[0] = Part{h->xcat, Gl, h->d1, Hdl, T};
-      np = 1;
-    } else {
-      parts[0] = Part{h->xcat, Gl, h->d1, Hdl, real0};
-      parts[1] = Part{x, lx, h->d1 + static_cast<size_t>(real0) * Hdl, Hdl, Bl};
-      np = 2;
-    }
-    TRY(run_gemm(h, true, true, parts, np, h->Gr(T_W1), ldw1, G, Hd, epi_none(), nullptr, 0, s));
-  }
+  TRY(gemm1(h, true, true, h->xcat, Gl, h->d1, Hdl, h->Gr(T_W1), ldw1, G, Hd, T, epi_none(), s));
   TRY(gemm1(h, true, true, h->h1, Hdl, h->d2, Hdl, h->Gr(T_W2), ldw2, Hd, Hd, T, epi_none(), s));
   {
     ColsumJob jobs[3];
@@ -1199,32 +1249,35 @@ static int generator_phase_a(wgan_handle* h, const float* z_dev, int ldz, int ro
   return generator_forward(h, h->zbuf, h->Zl, rows, h->xcat, h->Gl, s);
 }
 
-int wgan_generator_prepare(wgan_handle* h, const float* z_dev, int ldz, int rows, wgan_stream_t stream) {
+int wgan_generator_prepare(wgan_handle* h, const float* z_dev, int ldz, int rows, wgan_stream_t stream,
+                           uint64_t* token_out) {
   if (!h) return -2;
+  if (token_out) *token_out = 0;
   if (!z_dev) FAIL("generator_prepare: null input");
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
-  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
+  invalidate_workspace(h);
   h->sm_cap = h->num_sms - h->prepare_reserve;
   const int rc = generator_phase_a(h, z_dev, ldz, rows, static_cast<cudaStream_t>(stream));
   h->sm_cap = h->num_sms;
   TRY(rc);
-  h->gprep_z = z_dev; h->gprep_rows = rows;
+  h->gprep_token = h->ws_gen; h->gprep_rows = rows;
+  if (token_out) *token_out = h->gprep_token;
   return 0;
 }
 
 int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, int global_batch,
-                         wgan_stream_t stream) {
+                         uint64_t prepared_token, wgan_stream_t stream) {
   if (!h) return -2;
   if (!z_dev) FAIL("generator_grads: null input");
   TRY(check_rows(h, rows, global_batch));
   CK(cudaSetDevice(h->cfg.device));
-  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;   // this call reuses the activation workspace
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Bl = rows, Hd = h->Hd, Hdl = h->Hdl, G = h->G, Gl = h->Gl, Hg = h->Hg, Hgl = h->Hgl;
   const float a = h->cfg.alpha, invB = 1.0f / static_cast<float>(global_batch);
-  const bool prepared = (h->gprep_z == z_dev && h->gprep_rows == rows);
-  h->gprep_z = nullptr; h->gprep_rows = 0;
+  const bool prepared = prepared_token != 0 && prepared_token == h->gprep_token && prepared_token == h->ws_gen &&
+                        h->gprep_rows == rows;
+  invalidate_workspace(h);
   if (!prepared) TRY(generator_phase_a(h, z_dev, ldz, rows, s));
   const float* z = h->zbuf; const int lz = h->Zl;
   float* xt = h->xcat;
@@ -1272,6 +1325,99 @@ int wgan_generator_apply(wgan_handle* h, wgan_stream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Data parallelism: rendezvous + the engine's own all-reduce over NVLink peer memory
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DpBlob {                      // WGAN_DP_BLOB_BYTES, opaque to the caller
+  uint32_t magic;
+  int32_t rank, world, device;
+  int64_t pid;
+  uint64_t ptr;                      // window base in the exporting process
+  uint64_t win_bytes;
+  uint64_t arena_n[2];
+  int32_t blocks;
+  int32_t pad;
+  cudaIpcMemHandle_t ipc;            // 64 bytes
+};
+static_assert(sizeof(DpBlob) <= WGAN_DP_BLOB_BYTES, "DpBlob must fit the rendezvous blob");
+static_assert(DP_MAX_WORLD == WGAN_DP_MAX_WORLD, "kernel and ABI disagree on the maximum group size");
+constexpr uint32_t kDpMagic = 0x57474450u;   // "WGDP"
+}  // namespace
+
+int wgan_dp_export(wgan_handle* h, void* blob_out) {
+  if (!h) return -2;
+  if (!blob_out) FAIL("dp_export: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  DpBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = kDpMagic; b.rank = h->dp_rank; b.world = h->dp_world; b.device = h->cfg.device;
+  b.pid = static_cast<int64_t>(getpid());
+  b.ptr = reinterpret_cast<uint64_t>(h->dp_win);
+  b.win_bytes = h->dp_win_bytes;
+  b.arena_n[0] = h->arena_n[0]; b.arena_n[1] = h->arena_n[1];
+  b.blocks = h->dp_blocks;
+  CK(cudaIpcGetMemHandle(&b.ipc, h->dp_win));
+  memset(blob_out, 0, WGAN_DP_BLOB_BYTES);
+  memcpy(blob_out, &b, sizeof b);
+  return 0;
+}
+
+int wgan_dp_connect(wgan_handle* h, const void* blobs) {
+  if (!h) return -2;
+  if (!blobs) FAIL("dp_connect: null argument");
+  if (h->dp_world <= 1) { h->dp_connected = true; return 0; }
+  if (h->dp_connected) FAIL("dp_connect: already connected");
+  CK(cudaSetDevice(h->cfg.device));
+  const int64_t me = static_cast<int64_t>(getpid());
+  for (int r = 0; r < h->dp_world; ++r) {
+    DpBlob b;
+    memcpy(&b, static_cast<const char*>(blobs) + static_cast<size_t>(r) * WGAN_DP_BLOB_BYTES, sizeof b);
+    if (b.magic != kDpMagic || b.rank != r || b.world != h->dp_world)
+      FAIL("dp_connect: blob %d is not rank %d of a %d-rank group", r, r, h->dp_world);
+    if (b.win_bytes != h->dp_win_bytes || b.arena_n[0] != h->arena_n[0] || b.arena_n[1] != h->arena_n[1] ||
+        b.blocks != h->dp_blocks)
+      FAIL("dp_connect: rank %d was created with a different model configuration", r);
+    if (r == h->dp_rank) continue;
+    if (b.pid == me) {
+      // same process (one host thread per GPU, or several handles on one GPU): the pointer is directly usable
+      if (b.device != h->cfg.device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, h->cfg.device, b.device));
+        if (!can) FAIL("dp_connect: device %d cannot access device %d", h->cfg.device, b.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        (void)cudaGetLastError();
+      }
+      h->dp_peer[r] = reinterpret_cast<float*>(b.ptr);
+    } else {
+      void* mapped = nullptr;
+      CK(cudaIpcOpenMemHandle(&mapped, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->dp_peer[r] = static_cast<float*>(mapped);
+      h->dp_peer_ipc[r] = true;
+    }
+  }
+  h->dp_connected = true;
+  return 0;
+}
+
+int wgan_allreduce_grads(wgan_handle* h, int net, wgan_stream_t stream) {
+  if (!h) return -2;
+  if (net < 0 || net > 1) FAIL("allreduce_grads: bad net");
+  if (h->dp_world <= 1) return 0;
+  if (!h->dp_connected) FAIL("allreduce_grads: call wgan_dp_connect first");
+  CK(cudaSetDevice(h->cfg.device));
+  DpParams p;
+  memset(&p, 0, sizeof p);
+  for (int r = 0; r < h->dp_world; ++r) p.peer[r] = h->dp_peer[r];
+  p.rank = h->dp_rank; p.world = h->dp_world;
+  p.grad_off = h->dp_grad_off[net];
+  p.flags_off = h->dp_flags_off;
+  p.n4 = h->arena_n[net] / 4;
+  KLAUNCH(dp_allreduce_kernel, h->dp_blocks, 512, 0, static_cast<cudaStream_t>(stream), p);
+  return post_launch(h, "dp_allreduce_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched sampler: out = G(z)   (generator forward only, [W:217])
 // ---------------------------------------------------------------------------------------------
 int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int ld_out, int rows,
@@ -1280,7 +1426,7 @@ int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int
   if (!z_dev || !out_dev) FAIL("sample: null argument");
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
-  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
+  invalidate_workspace(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const float* z; int lz;
   TRY(stage_input(h, z_dev, ldz, rows, h->Z, h->zbuf, h->Zl, &z, &lz, s));
@@ -1301,7 +1447,7 @@ int wgan_critic_forward(wgan_handle* h, const float* x_dev, int ldx, float* d_ou
   if (!x_dev || !d_out_dev) FAIL("critic_forward: null argument");
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
-  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
+  invalidate_workspace(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Hd = h->Hd, Hdl = h->Hdl;
   const float a = h->cfg.alpha;
@@ -1328,7 +1474,7 @@ int wgan_latent_fit_step(wgan_handle* h, float* z_dev, float* m_dev, float* v_de
   if ((reinterpret_cast<uintptr_t>(z_dev) & 15) != 0) FAIL("latent_fit_step: z must be 16-byte aligned");
   TRY(check_rows(h, rows, rows));
   CK(cudaSetDevice(h->cfg.device));
-  h->prep_x = h->prep_z = h->prep_eps = nullptr; h->prep_rows = 0;
+  invalidate_workspace(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Bl = rows, G = h->G, Gl = h->Gl, Hg = h->Hg, Hgl = h->Hgl, Z = h->Z;
   const float a = h->cfg.alpha;

@@ -22,8 +22,10 @@
 // Shared-memory layouts: K-major tiles are SWIZZLE_128B boxes [rows][32 k]; MN-major 32-bit tiles must be
 // SWIZZLE_128B_BASE32B (TMA 128B_ATOM_32B) and come from a 3-D map (32 floats, K, MN/32) as one box
 // [chunk][32 k][32 mn].  Ragged M / N / K are handled by TMA zero fill and store clipping.
-// The epilogue (applied when splits == 1; split-K partials are finished by finish_splitk_* in kernels.cuh
-// with the same EpiParams) is
+// Long reductions with few output tiles run as stream-K in the CTA-pair kernel (one contiguous range of
+// (tile, K block) units per pair; partial accumulators meet in a workspace, the tile's owner applies the fused
+// epilogue).  The epilogue (applied when splits == 1; split-K partials, kept for raw-slab callers and the
+// single-CTA kernel, are finished by finish_splitk_* in kernels.cuh with the same EpiParams) is
 //      y = acc (+ bias[n]);  y = leaky_relu(y);  y *= slope(aux[m,n]);  y *= row_scale[m]
 //      row_sumsq[tile][m] = sum_n y^2;   optional second output  y2 = eps[m] * x[m,n] + (1 - eps[m]) * y
 // where slope(h) = h > 0 ? 1 : alpha recovers phi'(a) from the post-activation.  The [M, N] side
@@ -90,6 +92,14 @@ struct GemmParams {
   int side_mode;            // 0: side operand (if any) read with per-thread global loads; 1: TMA-staged
   int msub;                 // 128-row sub-tiles per CTA tile (1 or 2): 2 halves the B bytes per FLOP
   int nacc;                 // TMEM accumulator stages: 2 if 2 * msub * bn <= 512 columns, else 1
+  // stream-K (CTA-pair kernel only): the (tile, K block) units of the whole product are cut into ONE contiguous
+  // range per CTA pair, so every pair streams the same number of K blocks whatever the tile count.  A range that
+  // starts inside a tile leaves its accumulator in `sk_ws` (+ flag); the pair that holds the tile's first K block
+  // adds those partials in a fixed order and runs the fused epilogue: no split-K slabs, no finish pass.
+  int streamk;              // 0 = tiles (x splits) round-robin, 1 = stream-K
+  long long sk_units;       // m_tiles * n_tiles * total_kb
+  float* sk_ws;             // partial accumulators [pair][cta 2][chunk 8][j 8][row 128] float4
+  unsigned int* sk_flags;   // [pair][cta 2][epilogue warp]: 1 = that warp's share of the partial is written
   EpiParams epi;
 };
 
@@ -318,6 +328,299 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stream-K bookkeeping (CTA-pair kernel).  Units are (tile, K block) pairs in tile-major order; pair q owns
+// units [q * U / P, (q + 1) * U / P).  Its first segment may start inside a tile (kb0 > 0): that accumulator is a
+// PARTIAL, written to the pair's workspace slot.  A segment that starts a tile but does not finish it makes the
+// pair the tile's OWNER: it waits for the partials of the following pairs (each of which produced it as its very
+// first segment, long before), adds them in pair order and runs the fused epilogue.  Partial writers never wait
+// before their partial is out, and pairs are numbered against the block index (see the kernel), so there is no
+// cycle and no co-residency requirement.
+// ---------------------------------------------------------------------------------------------
+constexpr int SK_SLOT_FLOATS = 8 * 8 * 128 * 4;          // [chunk 8][j 8][row 128] float4 per CTA
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct Work {
+  int mn;                 // m/n tile index (nt = mn % n_tiles, mt = mn / n_tiles)
+  int z;                  // split slab of the output map (0 unless split-K)
+  int kb0, kb1;           // K blocks [kb0, kb1)
+  int sk_mode;            // 0 = complete accumulator, 1 = partial (write to workspace), 2 = owner (add partials)
+  int c_first, c_end;     // sk_mode 2: contributing pairs [c_first, c_end)
+};
+struct Sched {
+  int tile, step;         // round-robin over tiles x splits
+  long long u, u_end;     // stream-K unit range of this pair
+};
+__device__ __forceinline__ long long sk_first_unit(const GemmParams& p, int pair, int npairs) {
+  return static_cast<long long>(pair) * p.sk_units / npairs;
+}
+__device__ __forceinline__ void sched_init(const GemmParams& p, Sched& s, int pair, int npairs) {
+  s.tile = pair; s.step = npairs;
+  s.u = s.u_end = 0;
+  if (p.streamk) { s.u = sk_first_unit(p, pair, npairs); s.u_end = sk_first_unit(p, pair + 1, npairs); }
+}
+// Next work item of this pair; identical (warp-uniform) in the producer, the MMA issuer and every epilogue warp.
+__device__ __forceinline__ bool sched_next(const GemmParams& p, Sched& s, int pair, int npairs, Work& w) {
+  const int mn_tiles = p.m_tiles * p.n_tiles;
+  if (!p.streamk) {
+    if (s.tile >= mn_tiles * p.splits) return false;
+    w.mn = s.tile % mn_tiles;
+    w.z = s.tile / mn_tiles;
+    w.kb0 = w.z * p.kb_per_split;
+    w.kb1 = min(w.kb0 + p.kb_per_split, p.total_kb);
+    w.sk_mode = 0; w.c_first = w.c_end = 0;
+    s.tile += s.step;
+    return true;
+  }
+  if (s.u >= s.u_end) return false;
+  const int KB = p.total_kb;
+  w.mn = static_cast<int>(s.u / KB);
+  w.z = 0;
+  w.kb0 = static_cast<int>(s.u - static_cast<long long>(w.mn) * KB);
+  const long long left = s.u_end - s.u;
+  w.kb1 = (left < KB - w.kb0) ? w.kb0 + static_cast<int>(left) : KB;
+  s.u += w.kb1 - w.kb0;
+  w.c_first = w.c_end = 0;
+  if (w.kb0 > 0) {
+    w.sk_mode = 1;
+  } else if (w.kb1 == KB) {
+    w.sk_mode = 0;
+  } else {
+    w.sk_mode = 2;
+    const long long tile_end = static_cast<long long>(w.mn + 1) * KB;
+    w.c_first = pair + 1;
+    int c = pair + 1;
+    while (c < npairs && sk_first_unit(p, c, npairs) < tile_end) ++c;
+    w.c_end = c;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue of one accumulator, shared by both kernels: this warp's 32 rows (TMEM lane quadrant q) x its share of
+// the tile's 32-column chunks.  TMEM -> registers -> fused math -> swizzled smem box -> TMA store.
+// ---------------------------------------------------------------------------------------------
+struct EpiWarp {
+  uint32_t tmem_base, epi_base, side_base, side_bar;
+  int q, ew, cpart, lane;
+  uint32_t nstore, side_issued, side_waited;       // ring positions of the staging boxes / TMA-staged side boxes
+};
+
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, int nt, int z, int row0,
+                                              uint32_t tcol0, int sk_mode, int sk_cta, int sk_pair, int c_first,
+                                              int c_end) {
+  constexpr int CPARTS = NUM_EPI_WARPS / 4;
+  const EpiParams& e = p.epi;
+  const int lane = w.lane, q = w.q, ew = w.ew, cpart = w.cpart;
+  const bool fused = (p.splits == 1) && sk_mode != 1;
+  const bool side = fused && p.side_mode != 0;
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  float rs = 1.0f;
+  if (fused && e.row_scale != nullptr && row_ok) rs = __ldg(e.row_scale + row);
+  const bool bias_vec = (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
+  const bool aux_vec = ((reinterpret_cast<uintptr_t>(e.aux) & 15) == 0) && ((e.ld_aux & 3) == 0);
+  const bool blend = fused && e.blend_x != nullptr;
+  const bool blend_vec = ((reinterpret_cast<uintptr_t>(e.blend_x) & 15) == 0) && ((e.ld_blend & 3) == 0);
+  const float beps = (blend && row_ok) ? __ldg(e.blend_eps + row) : 0.0f;
+  float sumsq = 0.0f;
+  if (sk_mode == 2) {                                  // the contributors' partials (this warp's share) are written
+    if (lane == 0) {
+      for (int pr = c_first; pr < c_end; ++pr) {
+        const unsigned int* f = p.sk_flags + (static_cast<size_t>(pr) * 2 + sk_cta) * NUM_EPI_WARPS + ew;
+        while (ld_acquire_gpu(f) == 0u) { }
+      }
+    }
+    __syncwarp();
+  }
+  if (row0 < p.M) {
+    const int nchunks = p.bn / 32;
+    if (side && nt * p.bn + cpart * 32 < p.N && cpart < nchunks) {   // side box of this warp's first chunk
+      if (lane == 0) {
+        const uint32_t sl = ew * EPI_NBUF + (w.side_issued % EPI_NBUF);
+        mbar_expect_tx(w.side_bar + 8 * sl, EPI_BOX_BYTES);
+        tma_load_2d(w.side_base + sl * EPI_BOX_BYTES, &p.tma_side, w.side_bar + 8 * sl, nt * p.bn + cpart * 32, row0);
+      }
+      ++w.side_issued;
+    }
+    for (int c = cpart; c < nchunks; c += CPARTS) {
+      const int n0 = nt * p.bn + c * 32;
+      if (n0 >= p.N) break;
+      float sv[32];                              // TMA-staged side operand of this chunk
+      uint32_t v[32];
+      tmem_ld32_issue(w.tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 + static_cast<uint32_t>(c * 32), v);
+      if (sk_mode == 1) {
+        // stream-K partial: raw accumulator to this CTA's workspace slot, 512 contiguous bytes per instruction
+        tmem_ld32_wait(v);
+        float4* dst = reinterpret_cast<float4*>(p.sk_ws + (static_cast<size_t>(sk_pair) * 2 + sk_cta) * SK_SLOT_FLOATS) +
+                      static_cast<size_t>(c) * 8 * 128 + (32 * q + lane);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j * 128] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        continue;
+      }
+      if (fused) {
+        // epilogue operands are fetched while the TMEM load is in flight
+        float t[32];
+        if (e.bias != nullptr) {
+          load_chunk32(e.bias, n0, p.N, bias_vec, 0.0f, t);
+          tmem_ld32_wait(v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + t[j]);
+        } else {
+          tmem_ld32_wait(v);
+        }
+        if (sk_mode == 2) {
+          // add the other pairs' partial accumulators of this tile, in pair order (deterministic)
+          for (int pr = c_first; pr < c_end; ++pr) {
+            const float4* src =
+                reinterpret_cast<const float4*>(p.sk_ws + (static_cast<size_t>(pr) * 2 + sk_cta) * SK_SLOT_FLOATS) +
+                static_cast<size_t>(c) * 8 * 128 + (32 * q + lane);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 u = __ldcg(src + j * 128);          // written by another SM during this launch: L2 only
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + u.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + u.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + u.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + u.w);
+            }
+          }
+        }
+        if (e.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float y = __uint_as_float(v[j]);
+            v[j] = __float_as_uint(fmaxf(y, e.alpha * y));
+          }
+        }
+        if (side) {
+          const uint32_t sl = ew * EPI_NBUF + (w.side_waited % EPI_NBUF);
+          mbar_wait(w.side_bar + 8 * sl, (w.side_waited / EPI_NBUF) & 1);
+          ++w.side_waited;
+          const uint32_t sb = w.side_base + sl * EPI_BOX_BYTES + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t r0, r1, r2, r3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                         : "r"(sb + (static_cast<uint32_t>(j ^ (lane & 7)) << 4))
+                         : "memory");
+            sv[4 * j] = __uint_as_float(r0); sv[4 * j + 1] = __uint_as_float(r1);
+            sv[4 * j + 2] = __uint_as_float(r2); sv[4 * j + 3] = __uint_as_float(r3);
+          }
+          // The refill below overwrites this box through the async proxy (TMA), which is not ordered after generic-
+          // proxy loads that have merely been ISSUED: without the proxy fence a late ld.shared could see the next
+          // chunk's data (measured: ~2e-4 of the boxes under shared-memory pressure, r02 xhat_probe).  The fence
+          // completes every lane's loads; the warp barrier then hands the slot to the elected lane.
+          fence_proxy_async_smem();
+          __syncwarp();                          // every lane has its values: the ring slot is free again
+          const int cn = c + CPARTS;             // prefetch the next chunk's box while this one is processed
+          if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
+            if (lane == 0) {
+              const uint32_t sn = ew * EPI_NBUF + (w.side_issued % EPI_NBUF);
+              mbar_expect_tx(w.side_bar + 8 * sn, EPI_BOX_BYTES);
+              tma_load_2d(w.side_base + sn * EPI_BOX_BYTES, &p.tma_side, w.side_bar + 8 * sn, nt * p.bn + cn * 32, row0);
+            }
+            ++w.side_issued;
+          }
+        }
+        if (e.aux != nullptr) {
+          if (!side) {
+            if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, sv);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sl = (row_ok && !(sv[j] > 0.0f)) ? e.alpha : 1.0f;
+            v[j] = __float_as_uint(__uint_as_float(v[j]) * sl);
+          }
+        }
+        if (e.row_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
+        }
+        if (e.row_sumsq != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float y = __uint_as_float(v[j]);
+            if (n0 + j < p.N) sumsq = fmaf(y, y, sumsq);
+          }
+        }
+      } else {
+        tmem_ld32_wait(v);
+      }
+      const uint32_t buf = w.epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (w.nstore % EPI_NBUF)) * EPI_BOX_BYTES);
+      if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();   // the box used EPI_NBUF stores ago is free again
+      __syncwarp();
+      const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t a = rbase + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);   // SWIZZLE_128B
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
+                     "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&p.tma_d, buf, n0, row0, z);
+        tma_store_commit();
+      }
+      ++w.nstore;
+      if (blend) {
+        if (!side) {
+          if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, sv);
+        }
+        const float om = 1.0f - beps;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = __float_as_uint(row_ok ? beps * sv[j] + om * __uint_as_float(v[j]) : 0.0f);
+        const uint32_t buf2 = w.epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (w.nstore % EPI_NBUF)) * EPI_BOX_BYTES);
+        if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
+        __syncwarp();
+        const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = rb2 + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
+                       "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&p.tma_d2, buf2, n0, row0, z);
+          tma_store_commit();
+        }
+        ++w.nstore;
+      }
+    }
+  }
+  if (fused && e.row_sumsq != nullptr && row_ok)
+    e.row_sumsq[static_cast<size_t>(nt * CPARTS + cpart) * p.M + row] = sumsq;
+  if (sk_mode == 1) {
+    // publish this warp's share of the partial: every lane's stores, then the flag (release)
+    __threadfence();
+    __syncwarp();
+    if (lane == 0)
+      st_release_gpu(p.sk_flags + (static_cast<size_t>(sk_pair) * 2 + sk_cta) * NUM_EPI_WARPS + ew, 1u);
+  } else if (sk_mode == 2) {
+    // every lane has consumed the partials: rearm the flags for the next launch
+    __syncwarp();
+    if (lane == 0)
+      for (int pr = c_first; pr < c_end; ++pr)
+        p.sk_flags[(static_cast<size_t>(pr) * 2 + sk_cta) * NUM_EPI_WARPS + ew] = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The kernel.  Dynamic smem (after 1024 B alignment):
 //   [stages] x { A tile (128 * msub) x 128 B | B tile bn x 128 B }, 8 x 4 KB epilogue boxes,
 //   full[8], empty[8], tmem_full[2], tmem_empty[2] mbarriers, tmem base pointer.
@@ -506,15 +809,13 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
     }
   } else {
     // ===================== epilogue warps (TMEM -> regs -> smem -> TMA store) =====================
-    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
-    const int ew = warp - 2;                       // epilogue warp index 0..NUM_EPI_WARPS-1
-    const int cpart = ew >> 2;                     // which share of the tile's 32-column chunks this warp drains
-    constexpr int CPARTS = NUM_EPI_WARPS / 4;
-    const EpiParams& e = p.epi;
-    const bool fused = (p.splits == 1);
-    uint32_t nstore = 0;
-    uint32_t side_issued = 0, side_waited = 0;     // per-warp ring of 2 TMA-staged side boxes
-    const bool side = (p.splits == 1) && p.side_mode != 0;
+    EpiWarp w;
+    w.tmem_base = tmem_base; w.epi_base = epi_base; w.side_base = side_base; w.side_bar = side_bar;
+    w.q = warp & 3;                                // TMEM lane quadrant this warp may access
+    w.ew = warp - 2;                               // epilogue warp index 0..NUM_EPI_WARPS-1
+    w.cpart = w.ew >> 2;                           // which share of the tile's 32-column chunks this warp drains
+    w.lane = lane;
+    w.nstore = 0; w.side_issued = 0; w.side_waited = 0;
     int it = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int nt = tile % p.n_tiles;
@@ -524,154 +825,9 @@ gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
       const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tcgen05_after_sync();
-      for (int sub = 0; sub < p.msub; ++sub) {
-      const int row0 = mt * TM + sub * BM + 32 * q;
-      const int row = row0 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t tcol0 = static_cast<uint32_t>((acc * p.msub + sub) * p.bn);
-      float rs = 1.0f;
-      if (fused && e.row_scale != nullptr && row_ok) rs = __ldg(e.row_scale + row);
-      const bool bias_vec = (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
-      const bool aux_vec = ((reinterpret_cast<uintptr_t>(e.aux) & 15) == 0) && ((e.ld_aux & 3) == 0);
-      const bool blend = fused && e.blend_x != nullptr;
-      const bool blend_vec = ((reinterpret_cast<uintptr_t>(e.blend_x) & 15) == 0) && ((e.ld_blend & 3) == 0);
-      const float beps = (blend && row_ok) ? __ldg(e.blend_eps + row) : 0.0f;
-      float sumsq = 0.0f;
-      if (row0 < p.M) {
-        const int nchunks = p.bn / 32;
-        if (side && nt * p.bn + cpart * 32 < p.N && cpart < nchunks) {   // side box of this warp's first chunk
-          if (lane == 0) {
-            const uint32_t sl = ew * EPI_NBUF + (side_issued % EPI_NBUF);
-            mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
-            tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cpart * 32, row0);
-          }
-          ++side_issued;
-        }
-        for (int c = cpart; c < nchunks; c += CPARTS) {
-          const int n0 = nt * p.bn + c * 32;
-          if (n0 >= p.N) break;
-          float sv[32];                              // TMA-staged side operand of this chunk
-          uint32_t v[32];
-          tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 +
-                              static_cast<uint32_t>(c * 32), v);
-          if (fused) {
-            // epilogue operands are fetched while the TMEM load is in flight
-            float t[32];
-            if (e.bias != nullptr) {
-              load_chunk32(e.bias, n0, p.N, bias_vec, 0.0f, t);
-              tmem_ld32_wait(v);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + t[j]);
-            } else {
-              tmem_ld32_wait(v);
-            }
-            if (e.act == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float y = __uint_as_float(v[j]);
-                v[j] = __float_as_uint(fmaxf(y, e.alpha * y));
-              }
-            }
-            if (side) {
-              const uint32_t sl = ew * EPI_NBUF + (side_waited % EPI_NBUF);
-              mbar_wait(side_bar + 8 * sl, (side_waited / EPI_NBUF) & 1);
-              ++side_waited;
-              const uint32_t sb = side_base + sl * EPI_BOX_BYTES + static_cast<uint32_t>(lane) * 128u;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                uint32_t r0, r1, r2, r3;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                             : "r"(sb + (static_cast<uint32_t>(j ^ (lane & 7)) << 4))
-                             : "memory");
-                sv[4 * j] = __uint_as_float(r0); sv[4 * j + 1] = __uint_as_float(r1);
-                sv[4 * j + 2] = __uint_as_float(r2); sv[4 * j + 3] = __uint_as_float(r3);
-              }
-              __syncwarp();                          // every lane has its values: the ring slot is free again
-              const int cn = c + CPARTS;             // prefetch the next chunk's box while this one is processed
-              if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
-                if (lane == 0) {
-                  const uint32_t sn = ew * EPI_NBUF + (side_issued % EPI_NBUF);
-                  mbar_expect_tx(side_bar + 8 * sn, EPI_BOX_BYTES);
-                  tma_load_2d(side_base + sn * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sn, nt * p.bn + cn * 32, row0);
-                }
-                ++side_issued;
-              }
-            }
-            if (e.aux != nullptr) {
-              if (!side) {
-                if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, sv);
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float sl = (row_ok && !(sv[j] > 0.0f)) ? e.alpha : 1.0f;
-                v[j] = __float_as_uint(__uint_as_float(v[j]) * sl);
-              }
-            }
-            if (e.row_scale != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
-            }
-            if (e.row_sumsq != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float y = __uint_as_float(v[j]);
-                if (n0 + j < p.N) sumsq = fmaf(y, y, sumsq);
-              }
-            }
-          } else {
-            tmem_ld32_wait(v);
-          }
-          const uint32_t buf = epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (nstore % EPI_NBUF)) * EPI_BOX_BYTES);
-          if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();   // the box used EPI_NBUF stores ago is free again
-          __syncwarp();
-          const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t a = rbase + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);   // SWIZZLE_128B
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
-                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                         : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&p.tma_d, buf, n0, row0, z);
-            tma_store_commit();
-          }
-          ++nstore;
-          if (blend) {
-            if (!side) {
-              if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, sv);
-            }
-            const float om = 1.0f - beps;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = __float_as_uint(row_ok ? beps * sv[j] + om * __uint_as_float(v[j]) : 0.0f);
-            const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (nstore % EPI_NBUF)) * EPI_BOX_BYTES);
-            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
-            __syncwarp();
-            const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t a = rb2 + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
-                           "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                           : "memory");
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&p.tma_d2, buf2, n0, row0, z);
-              tma_store_commit();
-            }
-            ++nstore;
-          }
-        }
-      }
-      if (fused && e.row_sumsq != nullptr && row_ok)
-        e.row_sumsq[static_cast<size_t>(nt * CPARTS + cpart) * p.M + row] = sumsq;
-      }  // sub
+      for (int sub = 0; sub < p.msub; ++sub)
+        epilogue_tile(p, w, nt, z, mt * TM + sub * BM + 32 * w.q, static_cast<uint32_t>((acc * p.msub + sub) * p.bn),
+                      0, 0, 0, 0, 0);
       // all of this warp's TMEM reads for the tile are done: hand the accumulator back
       tcgen05_before_sync();
       __syncwarp();
@@ -795,26 +951,30 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
   pdl_wait();                                  // everything above overlapped the previous kernel's tail
 
-  // Persistent schedule over "cluster tiles": the C CTAs of a cluster take C consecutive M tiles of
-  // the same N tile and split, and walk the K blocks in lockstep.
+  // Persistent schedule: pair tiles (x split-K slabs) round-robin, or one contiguous stream-K unit range per pair;
+  // the three warp roles walk the same sched_next sequence.
   const uint32_t crank = cluster_ctarank();
   const uint16_t cmask = 3;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;      // pair tiles
-  const int tile0 = blockIdx.x / 2, tile_step = gridDim.x / 2;
+  // work items come from sched_next (tiles or stream-K).  Stream-K numbers the pairs AGAINST the block index: a
+  // tile's owner waits for the partials of HIGHER pairs only, i.e. of blocks launched before it, so any prefix of
+  // the grid that is resident can finish on its own -- no co-residency requirement, whatever else holds SMs.
+  const int npairs = gridDim.x / 2;
+  const int pair = p.streamk ? npairs - 1 - static_cast<int>(blockIdx.x / 2) : static_cast<int>(blockIdx.x / 2);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     const uint32_t full_leader = mapa_cluster(full_bar, 0);       // all loads signal the leader's barrier
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-      const int nt = tile % p.n_tiles;
-      const int mt = (tile / p.n_tiles) % p.m_tiles;
-      const int z = tile / (p.n_tiles * p.m_tiles);
+    Sched sc;
+    sched_init(p, sc, pair, npairs);
+    Work wk;
+    while (sched_next(p, sc, pair, npairs, wk)) {
+      const int nt = wk.mn % p.n_tiles;
+      const int mt = wk.mn / p.n_tiles;
       const int m0 = mt * TM + static_cast<int>(crank) * BM;      // this CTA's 128 rows
       const int n0 = nt * p.bn + static_cast<int>(crank) * (p.bn / 2);   // this CTA's half of the B tile
-      const int kb0 = z * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+      const int kb0 = wk.kb0, kb1 = wk.kb1;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
         const uint32_t fb = full_leader + 8 * stage;
@@ -870,10 +1030,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
-      const int z = tile / (p.n_tiles * p.m_tiles);
-      const int kb0 = z * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+    Sched sc;
+    sched_init(p, sc, pair, npairs);
+    Work wk;
+    for (; sched_next(p, sc, pair, npairs, wk); ++it) {
+      const int kb0 = wk.kb0, kb1 = wk.kb1;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
@@ -901,172 +1062,26 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
     __syncwarp();
   } else {
     // ===================== epilogue warps (TMEM -> regs -> smem -> TMA store) =====================
-    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
-    const int ew = warp - 2;                       // epilogue warp index 0..NUM_EPI_WARPS-1
-    const int cpart = ew >> 2;                     // which share of the tile's 32-column chunks this warp drains
-    constexpr int CPARTS = NUM_EPI_WARPS / 4;
-    const EpiParams& e = p.epi;
-    const bool fused = (p.splits == 1);
-    uint32_t nstore = 0;
-    uint32_t side_issued = 0, side_waited = 0;     // per-warp ring of 2 TMA-staged side boxes
-    const bool side = (p.splits == 1) && p.side_mode != 0;
+    EpiWarp w;
+    w.tmem_base = tmem_base; w.epi_base = epi_base; w.side_base = side_base; w.side_bar = side_bar;
+    w.q = warp & 3;                                // TMEM lane quadrant this warp may access
+    w.ew = warp - 2;                               // epilogue warp index 0..NUM_EPI_WARPS-1
+    w.cpart = w.ew >> 2;                           // which share of the tile's 32-column chunks this warp drains
+    w.lane = lane;
+    w.nstore = 0; w.side_issued = 0; w.side_waited = 0;
+    Sched sc;
+    sched_init(p, sc, pair, npairs);
+    Work wk;
     int it = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
-      const int nt = tile % p.n_tiles;
-      const int mt = (tile / p.n_tiles) % p.m_tiles;
-      const int z = tile / (p.n_tiles * p.m_tiles);
+    for (; sched_next(p, sc, pair, npairs, wk); ++it) {
+      const int nt = wk.mn % p.n_tiles;
+      const int mt = wk.mn / p.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tcgen05_after_sync();
-      {
-      const int row0 = mt * TM + static_cast<int>(crank) * BM + 32 * q;
-      const int row = row0 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t tcol0 = static_cast<uint32_t>(acc * p.bn);
-      float rs = 1.0f;
-      if (fused && e.row_scale != nullptr && row_ok) rs = __ldg(e.row_scale + row);
-      const bool bias_vec = (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
-      const bool aux_vec = ((reinterpret_cast<uintptr_t>(e.aux) & 15) == 0) && ((e.ld_aux & 3) == 0);
-      const bool blend = fused && e.blend_x != nullptr;
-      const bool blend_vec = ((reinterpret_cast<uintptr_t>(e.blend_x) & 15) == 0) && ((e.ld_blend & 3) == 0);
-      const float beps = (blend && row_ok) ? __ldg(e.blend_eps + row) : 0.0f;
-      float sumsq = 0.0f;
-      if (row0 < p.M) {
-        const int nchunks = p.bn / 32;
-        if (side && nt * p.bn + cpart * 32 < p.N && cpart < nchunks) {   // side box of this warp's first chunk
-          if (lane == 0) {
-            const uint32_t sl = ew * EPI_NBUF + (side_issued % EPI_NBUF);
-            mbar_expect_tx(side_bar + 8 * sl, EPI_BOX_BYTES);
-            tma_load_2d(side_base + sl * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sl, nt * p.bn + cpart * 32, row0);
-          }
-          ++side_issued;
-        }
-        for (int c = cpart; c < nchunks; c += CPARTS) {
-          const int n0 = nt * p.bn + c * 32;
-          if (n0 >= p.N) break;
-          float sv[32];                              // TMA-staged side operand of this chunk
-          uint32_t v[32];
-          tmem_ld32_issue(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tcol0 +
-                              static_cast<uint32_t>(c * 32), v);
-          if (fused) {
-            // epilogue operands are fetched while the TMEM load is in flight
-            float t[32];
-            if (e.bias != nullptr) {
-              load_chunk32(e.bias, n0, p.N, bias_vec, 0.0f, t);
-              tmem_ld32_wait(v);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + t[j]);
-            } else {
-              tmem_ld32_wait(v);
-            }
-            if (e.act == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float y = __uint_as_float(v[j]);
-                v[j] = __float_as_uint(fmaxf(y, e.alpha * y));
-              }
-            }
-            if (side) {
-              const uint32_t sl = ew * EPI_NBUF + (side_waited % EPI_NBUF);
-              mbar_wait(side_bar + 8 * sl, (side_waited / EPI_NBUF) & 1);
-              ++side_waited;
-              const uint32_t sb = side_base + sl * EPI_BOX_BYTES + static_cast<uint32_t>(lane) * 128u;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                uint32_t r0, r1, r2, r3;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                             : "r"(sb + (static_cast<uint32_t>(j ^ (lane & 7)) << 4))
-                             : "memory");
-                sv[4 * j] = __uint_as_float(r0); sv[4 * j + 1] = __uint_as_float(r1);
-                sv[4 * j + 2] = __uint_as_float(r2); sv[4 * j + 3] = __uint_as_float(r3);
-              }
-              __syncwarp();                          // every lane has its values: the ring slot is free again
-              const int cn = c + CPARTS;             // prefetch the next chunk's box while this one is processed
-              if (cn < nchunks && nt * p.bn + cn * 32 < p.N) {
-                if (lane == 0) {
-                  const uint32_t sn = ew * EPI_NBUF + (side_issued % EPI_NBUF);
-                  mbar_expect_tx(side_bar + 8 * sn, EPI_BOX_BYTES);
-                  tma_load_2d(side_base + sn * EPI_BOX_BYTES, &p.tma_side, side_bar + 8 * sn, nt * p.bn + cn * 32, row0);
-                }
-                ++side_issued;
-              }
-            }
-            if (e.aux != nullptr) {
-              if (!side) {
-                if (row_ok) load_chunk32(e.aux + static_cast<size_t>(row) * e.ld_aux, n0, p.N, aux_vec, 1.0f, sv);
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float sl = (row_ok && !(sv[j] > 0.0f)) ? e.alpha : 1.0f;
-                v[j] = __float_as_uint(__uint_as_float(v[j]) * sl);
-              }
-            }
-            if (e.row_scale != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
-            }
-            if (e.row_sumsq != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float y = __uint_as_float(v[j]);
-                if (n0 + j < p.N) sumsq = fmaf(y, y, sumsq);
-              }
-            }
-          } else {
-            tmem_ld32_wait(v);
-          }
-          const uint32_t buf = epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (nstore % EPI_NBUF)) * EPI_BOX_BYTES);
-          if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();   // the box used EPI_NBUF stores ago is free again
-          __syncwarp();
-          const uint32_t rbase = buf + static_cast<uint32_t>(lane) * 128u;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t a = rbase + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);   // SWIZZLE_128B
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
-                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                         : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&p.tma_d, buf, n0, row0, z);
-            tma_store_commit();
-          }
-          ++nstore;
-          if (blend) {
-            if (!side) {
-              if (row_ok) load_chunk32(e.blend_x + static_cast<size_t>(row) * e.ld_blend, n0, p.N, blend_vec, 0.0f, sv);
-            }
-            const float om = 1.0f - beps;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = __float_as_uint(row_ok ? beps * sv[j] + om * __uint_as_float(v[j]) : 0.0f);
-            const uint32_t buf2 = epi_base + static_cast<uint32_t>((ew * EPI_NBUF + (nstore % EPI_NBUF)) * EPI_BOX_BYTES);
-            if (lane == 0) tma_store_wait_read<EPI_NBUF - 1>();
-            __syncwarp();
-            const uint32_t rb2 = buf2 + static_cast<uint32_t>(lane) * 128u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t a = rb2 + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
-                           "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                           : "memory");
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&p.tma_d2, buf2, n0, row0, z);
-              tma_store_commit();
-            }
-            ++nstore;
-          }
-        }
-      }
-      if (fused && e.row_sumsq != nullptr && row_ok)
-        e.row_sumsq[static_cast<size_t>(nt * CPARTS + cpart) * p.M + row] = sumsq;
-      }
+      epilogue_tile(p, w, nt, wk.z, mt * TM + static_cast<int>(crank) * BM + 32 * w.q, static_cast<uint32_t>(acc * p.bn),
+                    wk.sk_mode, static_cast<int>(crank), pair, wk.c_first, wk.c_end);
       // all of this warp's TMEM reads for the tile are done: hand the accumulator back to the leader's MMA warp
       tcgen05_before_sync();
       __syncwarp();

@@ -1,7 +1,8 @@
 // Non-GEMM device kernels of the WGAN(-GP) hot path: split-K finish, FP32 verification GEMM,
 // critic head (layer-3 row dot + loss partials + delta/g2 construction), gradient-penalty
 // coefficient, interpolate blend, column sums (bias grads), fused multi-tensor TF-Adam,
-// Philox RNG (noise prior / epsilon / cell indices), row gather, latent-fit residual.
+// Philox RNG (noise prior / epsilon / cell indices), row gather, latent-fit residual, and the data-parallel
+// gradient all-reduce over NVLink peer memory.
 // Reference semantics: losses [W:137-138], LeakyReLU [W:69..117], Adam [A:140-151,214-225],
 // prior [W:91-94], minibatch gather [W:188-191].  Math per SURVEY Appendix A.
 #pragma once
@@ -780,6 +781,101 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __r
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
     dst[static_cast<size_t>(r) * ldd + c] = src[static_cast<size_t>(r) * lds + c];
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Data-parallel gradient exchange over NVLink peer memory: in-place SUM over `world` ranks of one
+// gradient arena (+ the loss scalars in its tail), one launch per rank, no NCCL.
+// Every rank maps every rank's window (gradient arenas + flags, one allocation).  Two-shot: rank r owns slice r of
+// the arena; block b of rank r
+//   1. tells every peer "my gradients are final" (arrive1[b][r] = epoch) and waits for the same from every peer,
+//   2. PULLS its part of slice r from every rank, adds the W values in rank order (so every replica ends up with
+//      bit-identical sums) and PUSHES the sum into every rank's arena,
+//   3. tells every peer "my pushes are out" (arrive2[b][r] = epoch) and waits for every peer's block b.
+// When all blocks of a rank have left step 3, all slices of its arena hold the global sum and nobody reads its
+// arena any more.  The epoch lives in the window (advanced by the kernel), so a CUDA-graph replay works.
+// Flags are system-scope release/acquire; gradient values cross NVLink as 16-byte relaxed.sys accesses.
+// ---------------------------------------------------------------------------------------------
+constexpr int DP_MAX_WORLD = 16;
+constexpr int DP_MAX_BLOCKS = 64;
+constexpr int DP_FLAG_WORDS = DP_MAX_BLOCKS * (2 * DP_MAX_WORLD + 1);   // arrive1, arrive2 [block][rank]; epoch[block]
+
+struct DpParams {
+  float* peer[DP_MAX_WORLD];     // window base of every rank, as mapped in this process
+  int rank, world;
+  size_t grad_off;               // floats from the window base to this net's gradient arena
+  size_t flags_off;              // floats from the window base to the flag words
+  size_t n4;                     // float4 groups in the arena (scalar tail included)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_v4(float4* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// One cross-GPU rendezvous of block b: publish `epoch` in slot [b][rank] of every rank's `which` array (0 =
+// arrive1, 1 = arrive2), then wait until every rank has published it here.  Called by all threads of the block.
+__device__ __forceinline__ void dp_rendezvous(const DpParams& p, int which, unsigned int epoch) {
+  __syncthreads();                                  // every thread's earlier accesses precede the release below
+  const int t = threadIdx.x;
+  if (t < p.world) {
+    const size_t slot = static_cast<size_t>(which) * DP_MAX_BLOCKS * DP_MAX_WORLD + blockIdx.x * DP_MAX_WORLD;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned int*>(p.peer[t] + p.flags_off) + slot + p.rank, epoch);
+    const unsigned int* mine = reinterpret_cast<const unsigned int*>(p.peer[p.rank] + p.flags_off) + slot + t;
+    while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) { }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512)
+dp_allreduce_kernel(const DpParams p) {
+  // no early griddepcontrol.launch_dependents: blocks of the next kernel parked on the SMs could keep a PEER's
+  // all-reduce blocks (same GPU, other stream: several handles on one device) from becoming resident while this
+  // grid spins on them
+  pdl_wait();
+  __shared__ unsigned int s_epoch;
+  unsigned int* my_flags = reinterpret_cast<unsigned int*>(p.peer[p.rank] + p.flags_off);
+  unsigned int* epoch_word = my_flags + 2 * DP_MAX_BLOCKS * DP_MAX_WORLD + blockIdx.x;
+  if (threadIdx.x == 0) s_epoch = *epoch_word + 1u;
+  __syncthreads();
+  const unsigned int epoch = s_epoch;
+  const int W = p.world;
+  dp_rendezvous(p, 0, epoch);
+  // this block's part of slice `rank`
+  const size_t lo = p.n4 * p.rank / W, hi = p.n4 * (p.rank + 1) / W;
+  const size_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
+  const size_t b0 = lo + per * blockIdx.x, b1 = b0 + per < hi ? b0 + per : hi;
+  for (size_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
+    float4 v[DP_MAX_WORLD];
+#pragma unroll
+    for (int k = 0; k < DP_MAX_WORLD; ++k)
+      if (k < W) v[k] = ld_relaxed_sys_v4(reinterpret_cast<const float4*>(p.peer[k] + p.grad_off) + i);
+    float4 acc = v[0];
+#pragma unroll
+    for (int k = 1; k < DP_MAX_WORLD; ++k)
+      if (k < W) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+#pragma unroll
+    for (int k = 0; k < DP_MAX_WORLD; ++k)
+      if (k < W) st_relaxed_sys_v4(reinterpret_cast<float4*>(p.peer[k] + p.grad_off) + i, acc);
+  }
+  dp_rendezvous(p, 1, epoch);
+  if (threadIdx.x == 0) *epoch_word = epoch;
+  pdl_launch_dependents();
 }
 
 // Latent fit (build-defined): r = G(z) - x; loss[b] = sum r^2; d3 = 2 r slope(G(z)).

@@ -88,13 +88,17 @@ def _stream() -> C.c_void_p:
 
 
 class WGANTrainer:
-    """One handle per GPU / per process.  Data-parallel when torch.distributed is initialised:
-    every rank passes its batch shard, gradients are SUM-all-reduced (one collective per
-    optimizer step over the flat gradient arena) and Adam runs replicated."""
+    """One handle per GPU / per process.  Data-parallel when torch.distributed is initialised (or when
+    ``dp_rank`` / ``dp_world`` are given and ``dp_connect`` is called by hand): every rank passes its batch shard,
+    gradients are SUM-all-reduced -- one exchange per optimizer step over the flat gradient arena, done by the
+    library's own kernel over NVLink peer memory (``wgan_allreduce_grads``) -- and Adam runs replicated.
+    ``torch.distributed`` only carries the 128-byte rendezvous blobs.  ``dp_backend="nccl"`` keeps the
+    round-1 ``torch.distributed.all_reduce`` exchange for A/B measurements."""
 
     def __init__(self, cfg: WGANConfig, max_batch: Optional[int] = None, device: Optional[int] = None,
                  gemm_mode: int = 0, optimizer: Optional[Adam_Prediction_Optimizer] = None,
-                 process_group=None, distributed: Optional[bool] = None):
+                 process_group=None, distributed: Optional[bool] = None, dp_rank: Optional[int] = None,
+                 dp_world: Optional[int] = None, dp_backend: Optional[str] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("WGANTrainer needs a CUDA device (B200); there is no CPU fallback")
         self.cfg = cfg
@@ -108,10 +112,24 @@ class WGANTrainer:
             self.cfg = cfg
         if cfg.gp_form not in ("explicit", "gram"):
             raise ValueError(f"gp_form must be 'explicit' or 'gram', got {cfg.gp_form!r}")
+        # data parallel plumbing: rank / world come from torch.distributed unless given explicitly
+        import torch.distributed as dist
+        self.dist = dist
+        use_dist = (dist.is_available() and dist.is_initialized()) if distributed is None else distributed
+        self.group = process_group
+        if dp_world is not None:
+            self.world, self.rank = int(dp_world), int(dp_rank or 0)
+            use_dist = False
+        else:
+            self.world = dist.get_world_size(process_group) if use_dist else 1
+            self.rank = dist.get_rank(process_group) if use_dist else 0
+        self.dp_backend = dp_backend or os.environ.get("WGAN_B200_DP_BACKEND", "engine")
+        if self.dp_backend not in ("engine", "nccl"):
+            raise ValueError(f"dp_backend must be 'engine' or 'nccl', got {self.dp_backend!r}")
         c = _lib.WganConfig(cfg.noise_input_size, cfg.inflate_to_size, cfg.gex_size, cfg.disc_internal_size,
                             self.max_batch, self.device, gemm_mode, 1 if cfg.gp_form == "gram" else 0,
                             cfg.learn_rate, cfg.beta1, cfg.beta2,
-                            cfg.epsilon, cfg.alpha, cfg.lambda_gp, 0.0, 0.0)
+                            cfg.epsilon, cfg.alpha, cfg.lambda_gp, self.rank, self.world)
         self._h = C.c_void_p()
         rc = self.lib.wgan_create(C.byref(c), C.byref(self._h))
         if rc != 0:
@@ -122,16 +140,14 @@ class WGANTrainer:
             self._ck(self.lib.wgan_get_tensor_info(self._h, i, C.byref(ti)), "get_tensor_info")
             self.info[ti.name.decode()] = (i, ti.net, ti.rows, ti.cols, ti.ld, ti.offset)
         self.Gl = self.lib.wgan_padded_ld(cfg.gex_size)
-        # data parallel plumbing
-        import torch.distributed as dist
-        self.dist = dist
-        use_dist = dist.is_available() and dist.is_initialized() if distributed is None else distributed
-        self.group = process_group
-        self.world = dist.get_world_size(process_group) if use_dist else 1
-        self.rank = dist.get_rank(process_group) if use_dist else 0
         self._grad_arena = {n: self.arena(n, KIND_GRAD) for n in (NET_GENERATOR, NET_CRITIC)}
         self._data = None
+        self._data_max_value = 1.0
         self._calls = 0
+        self._dp_connected = self.world == 1
+        self._comm_stream = None
+        if self.world > 1 and use_dist and self.dp_backend == "engine":
+            self._dp_connect_distributed()
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc, what):
@@ -228,40 +244,89 @@ class WGANTrainer:
         assert t.stride(1) == 1
         return C.c_void_p(t.data_ptr()), int(t.stride(0)), int(t.shape[0])
 
+    # ------------------------------------------------------------------ data parallelism
+    def dp_export(self) -> bytes:
+        """This rank's rendezvous blob (wgan_dp_export): hand the blobs of all ranks, in rank order, to dp_connect."""
+        buf = C.create_string_buffer(_lib.DP_BLOB_BYTES)
+        self._ck(self.lib.wgan_dp_export(self._h, buf), "dp_export")
+        return buf.raw
+
+    def dp_connect(self, blobs):
+        """Map the gradient windows of all ranks (wgan_dp_connect).  `blobs`: one bytes object per rank."""
+        assert len(blobs) == self.world
+        joined = b"".join(blobs)
+        self._ck(self.lib.wgan_dp_connect(self._h, C.c_char_p(joined)), "dp_connect")
+        self._dp_connected = True
+
+    def _dp_connect_distributed(self):
+        mine = torch.frombuffer(bytearray(self.dp_export()), dtype=torch.uint8)
+        backend = self.dist.get_backend(self.group)
+        if backend == "nccl":
+            mine = mine.to(f"cuda:{self.device}")
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine, group=self.group)
+        self.dp_connect([bytes(t.cpu().numpy().tobytes()) for t in parts])
+        self.dist.barrier(group=self.group)      # every rank has mapped every window before the first exchange
+
     def _allreduce(self, net: int, overlap=None):
-        """One SUM all-reduce of the flat gradient arena (+ loss scalars) per optimizer step.  `overlap` is
-        host code that enqueues work independent of the reduced gradients (the next update's input pipeline and
-        generator forward); it runs on the compute stream while NCCL reduces on its own stream."""
-        if self.world > 1:
+        """One SUM all-reduce of the flat gradient arena (+ loss scalars) per optimizer step
+        (wgan_allreduce_grads: the library's own kernel over NVLink peer memory).  `overlap` is host code that
+        enqueues work independent of the reduced gradients (the next update's input pipeline and generator
+        forward); with overlap the exchange runs on a second stream next to it."""
+        if self.world == 1:
+            if overlap is not None:
+                overlap()
+            return
+        if self.dp_backend == "nccl":
             work = self.dist.all_reduce(self._grad_arena[net], op=self.dist.ReduceOp.SUM, group=self.group,
                                         async_op=True)
             if overlap is not None:
                 overlap()
             work.wait()
-        elif overlap is not None:
-            overlap()
+            return
+        assert self._dp_connected, "data-parallel trainer: call dp_connect(blobs) before the first step"
+        if overlap is None or os.environ.get("WGAN_B200_DP_SERIAL"):
+            self._ck(self.lib.wgan_allreduce_grads(self._h, net, _stream()), "allreduce_grads")
+            if overlap is not None:
+                overlap()
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=f"cuda:{self.device}", priority=-1)
+        main = torch.cuda.current_stream()
+        self._comm_stream.wait_stream(main)
+        self._ck(self.lib.wgan_allreduce_grads(self._h, net, C.c_void_p(self._comm_stream.cuda_stream)),
+                 "allreduce_grads")
+        overlap()
+        main.wait_stream(self._comm_stream)
 
-    def critic_prepare(self, x, z, eps=None):
-        """Run the critic-parameter-independent part of the next critic_step(x, z, eps) now."""
+    def critic_prepare(self, x, z, eps=None) -> int:
+        """Run the critic-parameter-independent part of the next critic_step(x, z, eps) now; the returned token is
+        honoured by that critic_step as long as nothing else used the activation workspace in between."""
         xp, ldx, rows = self._mat(x, self.cfg.gex_size)
         zp, ldz, _ = self._mat(z, self.cfg.noise_input_size)
         ep = C.c_void_p(eps.data_ptr()) if eps is not None else C.c_void_p()
-        self._ck(self.lib.wgan_critic_prepare(self._h, xp, ldx, zp, ldz, ep, rows, _stream()), "critic_prepare")
+        tok = C.c_uint64(0)
+        self._ck(self.lib.wgan_critic_prepare(self._h, xp, ldx, zp, ldz, ep, rows, _stream(), C.byref(tok)),
+                 "critic_prepare")
+        return tok.value
 
     def scalars(self, net: int) -> np.ndarray:
         out = np.empty(4, np.float32)
         self._ck(self.lib.wgan_get_scalars(self._h, net, out.ctypes.data_as(C.c_void_p), _stream()), "get_scalars")
         return out
 
-    def generator_prepare(self, z):
+    def generator_prepare(self, z) -> int:
         """Run the critic-independent part (z staging, G(z)) of the next generator_step(z) now."""
         zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
-        self._ck(self.lib.wgan_generator_prepare(self._h, zp, ldz, rows, _stream()), "generator_prepare")
+        tok = C.c_uint64(0)
+        self._ck(self.lib.wgan_generator_prepare(self._h, zp, ldz, rows, _stream(), C.byref(tok)), "generator_prepare")
+        return tok.value
 
     def critic_step(self, x, z, eps=None, apply: bool = True, read: bool = True, global_batch: Optional[int] = None,
-                    overlap=None):
+                    overlap=None, token: Optional[int] = None):
         """One critic update [W:199]: gradients of obj_d (+GP), all-reduce, Adam.
-        x [rows, gex], z [rows, noise], eps [rows] are this rank's shard."""
+        x [rows, gex], z [rows, noise], eps [rows] are this rank's shard.  `token`: what critic_prepare returned
+        for exactly these inputs, unchanged since (the library ignores a stale token and redoes the work)."""
         xp, ldx, rows = self._mat(x, self.cfg.gex_size)
         zp, ldz, rz = self._mat(z, self.cfg.noise_input_size)
         assert rz == rows
@@ -269,7 +334,8 @@ class WGANTrainer:
         if eps is not None:
             assert eps.is_cuda and eps.dtype == torch.float32 and eps.numel() == rows and eps.is_contiguous()
         gb = rows * self.world if global_batch is None else int(global_batch)
-        self._ck(self.lib.wgan_critic_grads(self._h, xp, ldx, zp, ldz, ep, rows, gb, _stream()), "critic_grads")
+        self._ck(self.lib.wgan_critic_grads(self._h, xp, ldx, zp, ldz, ep, rows, gb, int(token or 0), _stream()),
+                 "critic_grads")
         self._allreduce(NET_CRITIC, overlap)
         if apply:
             self._ck(self.lib.wgan_critic_apply(self._h, _stream()), "critic_apply")
@@ -279,11 +345,13 @@ class WGANTrainer:
         wass = float(s[0] - s[1])                                       # obj_d [W:137]
         return {"wasserstein": wass, "gp": float(s[2]), "critic_loss": wass + float(s[2])}
 
-    def generator_step(self, z, apply: bool = True, read: bool = True, global_batch: Optional[int] = None):
+    def generator_step(self, z, apply: bool = True, read: bool = True, global_batch: Optional[int] = None,
+                       token: Optional[int] = None):
         """One generator update [W:196]: gradients of obj_g through the critic, all-reduce, Adam."""
         zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
         gb = rows * self.world if global_batch is None else int(global_batch)
-        self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, gb, _stream()), "generator_grads")
+        self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, gb, int(token or 0), _stream()),
+                 "generator_grads")
         self._allreduce(NET_GENERATOR)
         if apply:
             self._ck(self.lib.wgan_generator_apply(self._h, _stream()), "generator_apply")
@@ -421,7 +489,7 @@ class WGANTrainer:
                 return x, z, eps
             return self.draw_minibatch(batch, seed, base + k, counter=counter)
 
-        nxt = draw(0)
+        nxt, tok = draw(0), 0
         for k in range(cfg.n_critic):
             x, z, eps = nxt
             hold = {}
@@ -431,19 +499,21 @@ class WGANTrainer:
                 # or, after the last critic update, the noise + G(z) of the generator update
                 if k + 1 < cfg.n_critic:
                     hold["n"] = draw(k + 1)
-                    self.critic_prepare(*hold["n"])
+                    hold["tok"] = self.critic_prepare(*hold["n"])
                 else:
-                    hold["zg"] = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic, counter=counter)
-                    self.generator_prepare(hold["zg"])
+                    hold["zg"] = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic, counter=counter,
+                                                  data_max_value=self._data_max_value)
+                    hold["tok"] = self.generator_prepare(hold["zg"])
 
-            r = self.critic_step(x, z, eps, read=read, overlap=ahead if self.world > 1 else None)
+            r = self.critic_step(x, z, eps, read=read, overlap=ahead if self.world > 1 else None, token=tok)
             if self.world == 1:
                 ahead()
             nxt = hold.get("n")
             zg = hold.get("zg")
+            tok = hold["tok"]
             if read:
                 out.update(r)
-        r = self.generator_step(zg, read=read)
+        r = self.generator_step(zg, read=read, token=tok)
         if read:
             out.update(r)
         return out if read else None

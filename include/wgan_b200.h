@@ -11,12 +11,17 @@
  * the caller owns every buffer it passes in; the handle owns parameters, Adam state and
  * workspace; a handle is bound to one GPU and is not thread-safe.
  * All matrices are row-major FP32, one cell (sample) per row, `ld*` = leading dimension
- * in floats.  An input that is 16-byte aligned with ld % 4 == 0 is consumed in place by TMA (anything
- * else is staged through a padded copy); the real-cell matrix x of wgan_critic_grads is then also read
- * as a column-chunked operand whose last 32-column chunk may touch up to 124 bytes past the end of a row,
- * so an in-place x needs that much readable slack after its last row (any cudaMalloc / framework
- * allocator block provides it; WGANTrainer.real_slot() avoids the question).  GEMMs run as TF32 tcgen05 tensor-core kernels (gemm_mode 0) or as FP32
- * CUDA-core kernels (gemm_mode 1, verification only).
+ * in floats.  Caller buffers are only ever read inside their logical extent [rows, cols]: a latent matrix that is
+ * 16-byte aligned with ld % 4 == 0 is consumed in place by TMA, anything else -- and always the real-cell matrix
+ * x, which the weight gradient also reads column-chunked -- is copied into the handle's stacked activation buffer
+ * first (no copy when x already IS that slot: wgan_get_buffer "xcat", WGANTrainer.real_slot()).
+ * GEMMs run as TF32 tcgen05 tensor-core kernels (gemm_mode 0) or as FP32 CUDA-core kernels (gemm_mode 1,
+ * verification only).
+ *
+ * Data parallelism lives behind this ABI: every rank creates its handle with dp_rank / dp_world,
+ * exports a small blob (wgan_dp_export), the host exchanges the blobs by any means (MPI, torch.distributed, a
+ * file) and hands all of them to wgan_dp_connect; wgan_allreduce_grads then sums a gradient arena (+ the loss
+ * scalars in its tail) over the ranks in place with the engine's own kernel over NVLink peer memory.
  */
 #ifndef WGAN_B200_H
 #define WGAN_B200_H
@@ -49,9 +54,14 @@ typedef struct wgan_config {
   float epsilon;              /* [A:38] 1e-8 */
   float alpha;                /* tf.nn.leaky_relu default 0.2 [W:69] */
   float lambda_gp;            /* 0 => no penalty term (reference-literal [W:137]) */
-  float reserved1;
-  float reserved2;
+  int32_t dp_rank;            /* data-parallel rank of this handle, 0 <= dp_rank < dp_world (batch shard) */
+  int32_t dp_world;           /* number of data-parallel ranks; 0 or 1 = single GPU */
 } wgan_config;
+
+/* Data-parallel rendezvous blob: opaque to the caller, produced by wgan_dp_export on every rank, gathered in rank
+ * order and passed to wgan_dp_connect on every rank. */
+#define WGAN_DP_MAX_WORLD 16
+#define WGAN_DP_BLOB_BYTES 128
 
 enum { WGAN_NET_GENERATOR = 0, WGAN_NET_CRITIC = 1 };
 enum { WGAN_KIND_PARAM = 0, WGAN_KIND_GRAD = 1, WGAN_KIND_M = 2, WGAN_KIND_V = 3 };
@@ -93,23 +103,44 @@ int wgan_get_scalars(wgan_handle* h, int net, float* host4, wgan_stream_t stream
  * (ignored when lambda_gp == 0).  global_batch = total rows over all data-parallel ranks
  * (the 1/B of the means).  Fills the critic GRAD arena + scalars
  * {mean-part D_fake, mean-part D_real, GP}.  */
+/* prepared_token: 0, or the token wgan_critic_prepare returned for exactly these inputs (see below). */
 int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
-                      const float* eps_dev, int rows, int global_batch, wgan_stream_t stream);
+                      const float* eps_dev, int rows, int global_batch, uint64_t prepared_token,
+                      wgan_stream_t stream);
 /* Optional: run the part of the critic step that does not depend on the critic's parameters (input
- * staging, x~ = G(z), interpolates) ahead of time; the next wgan_critic_grads with the SAME x/z/eps/rows
- * skips it.  Lets a data-parallel host overlap it with the gradient all-reduce of the previous update. */
+ * staging, x~ = G(z), interpolates) ahead of time, e.g. while the previous update's gradients are being
+ * all-reduced.  *token_out identifies the prepared activations: pass it to the wgan_critic_grads call for the
+ * same x / z / eps / rows, whose contents must not have changed in between.  Any other entry point that reuses
+ * the activation workspace (sample, critic_forward, latent fit, another prepare, a generator step) invalidates
+ * the token; a stale or zero token is never an error, the work is simply redone. */
 int wgan_critic_prepare(wgan_handle* h, const float* x_dev, int ldx, const float* z_dev, int ldz,
-                        const float* eps_dev, int rows, wgan_stream_t stream);
+                        const float* eps_dev, int rows, wgan_stream_t stream, uint64_t* token_out);
 /* Adam update of the critic from its GRAD arena [A:140-151], then beta powers [A:214-225]. */
 int wgan_critic_apply(wgan_handle* h, wgan_stream_t stream);
 /* Generator gradients: d(obj_g)/d(g_params) through the critic [W:138,142,155];
  * scalar WGAN_S_DFAKE = mean-part of D(G(z)) (obj_g = -that). */
 int wgan_generator_grads(wgan_handle* h, const float* z_dev, int ldz, int rows, int global_batch,
-                         wgan_stream_t stream);
-/* Optional: stage z and run x~ = G(z) ahead of wgan_generator_grads(same z, rows) (overlap with the last
- * critic all-reduce in data-parallel runs). */
-int wgan_generator_prepare(wgan_handle* h, const float* z_dev, int ldz, int rows, wgan_stream_t stream);
+                         uint64_t prepared_token, wgan_stream_t stream);
+/* Optional: stage z and run x~ = G(z) ahead of wgan_generator_grads(same z, rows, token) (overlap with the last
+ * critic all-reduce in data-parallel runs); token rules as for wgan_critic_prepare. */
+int wgan_generator_prepare(wgan_handle* h, const float* z_dev, int ldz, int rows, wgan_stream_t stream,
+                           uint64_t* token_out);
 int wgan_generator_apply(wgan_handle* h, wgan_stream_t stream);
+
+/* ---- data parallelism: batch-sharded ranks, one SUM all-reduce of a net's gradient arena per optimizer step
+ *      (the step it sits inside: minimize = gradients -> [all-reduce] -> apply_adam, [W:154-155],
+ *      [A:140-151]).  The exchange is the engine's own kernel over NVLink peer memory (no NCCL): rank r pulls
+ *      slice r of every rank's arena, adds them in rank order and pushes the sum back into every arena, so all
+ *      replicas hold bit-identical gradients and stay bit-identical after Adam. ---- */
+/* Writes this rank's WGAN_DP_BLOB_BYTES rendezvous blob. */
+int wgan_dp_export(wgan_handle* h, void* blob_out);
+/* blobs: dp_world * WGAN_DP_BLOB_BYTES bytes, blob of rank i at offset i * WGAN_DP_BLOB_BYTES.  Maps the peers'
+ * gradient windows (cudaIpc across processes, direct peer access inside one process).  Collective: every rank
+ * must call it before the first wgan_allreduce_grads. */
+int wgan_dp_connect(wgan_handle* h, const void* blobs);
+/* In-place SUM over all ranks of net's GRAD arena (incl. the WGAN_S_* scalar tail); asynchronous on `stream`,
+ * collective (every rank calls it for the same net in the same order).  A no-op when dp_world <= 1. */
+int wgan_allreduce_grads(wgan_handle* h, int net, wgan_stream_t stream);
 
 /* ---- sampling: G(z) for a batch of cells (replaces the batch-1 loop [W:217-221]) ---- */
 int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int ld_out, int rows,

@@ -66,7 +66,7 @@ def _run(tr, layout, M, N, K, rng, bias=False, act=0, aux=False, row_scale=False
     out = Dd.cpu().numpy()[:, :N].astype(np.float64)
     scale = np.abs(ref).max() + 1e-30
     err = np.abs(out - ref).max() / scale
-    res = {"err": err}
+    res = {"err": err, "out": Dd.cpu().numpy()[:, :N].copy()}
     if sumsq:
         got = sq_d.cpu().numpy()[:tiles.value * M].reshape(tiles.value, M).sum(axis=0)
         want = (ref * ref).sum(axis=1)
@@ -89,7 +89,7 @@ def test_gemm_plain(mode, layout, M, N, K):
     tr = _trainer(mode)
     rng = np.random.default_rng(hash((layout, M, N, K)) % (2 ** 32))
     r = _run(tr, layout, M, N, K, rng)
-    assert r["err"] < TOL[mode], r
+    assert r["err"] < TOL[mode], r["err"]
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -99,7 +99,7 @@ def test_gemm_splitk(mode, layout, M, N, K, splits):
     tr = _trainer(mode)
     rng = np.random.default_rng(7)
     r = _run(tr, layout, M, N, K, rng, bias=True, act=1, splits=splits)
-    assert r["err"] < TOL[mode], r
+    assert r["err"] < TOL[mode], r["err"]
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -108,11 +108,11 @@ def test_gemm_epilogues(mode, splits):
     tr = _trainer(mode)
     rng = np.random.default_rng(11)
     r = _run(tr, "fwd", 200, 200, 300, rng, bias=True, act=1, splits=splits)
-    assert r["err"] < TOL[mode], r
+    assert r["err"] < TOL[mode], r["err"]
     r = _run(tr, "dgrad", 150, 200, 200, rng, aux=True, splits=splits)
-    assert r["err"] < TOL[mode], r
+    assert r["err"] < TOL[mode], r["err"]
     r = _run(tr, "fwd", 150, 200, 700, rng, aux=True, row_scale=True, splits=splits)
-    assert r["err"] < TOL[mode], r
+    assert r["err"] < TOL[mode], r["err"]
     r = _run(tr, "dgrad", 150, 700, 200, rng, sumsq=True, splits=splits)
     assert r["err"] < TOL[mode] and r["sq_err"] < 2 * TOL[mode], r
 
@@ -142,3 +142,46 @@ def test_gemm_random_ragged_shapes():
         assert r["err"] < 3e-3, (layout, M, N, K, kw, r)
         if kw["sumsq"]:
             assert r["sq_err"] < 6e-3, (layout, M, N, K, kw, r)
+
+
+# Stream-K (splits = -1 forces it): every CTA pair streams one contiguous range of (tile, K block) units; partial
+# accumulators meet in a workspace and the tile's owner applies the fused epilogue.
+STREAMK_SHAPES = [
+    # few tiles, long K: many contributors per tile (1 tile: all 74 pairs feed one owner)
+    ("fwd", 256, 200, 6605), ("fwd", 300, 200, 4000), ("wgrad", 661, 200, 4096), ("dgrad", 512, 96, 3000),
+    # the two layer-1 products of the critic update at batch 1024 (policy picks stream-K there, see below)
+    ("fwd", 3072, 200, 6605), ("wgrad", 6605, 200, 3072),
+    # ragged everything, multiple N tiles, units not divisible by the pair count
+    ("fwd", 1000, 700, 1111), ("dgrad", 777, 300, 2500), ("wgrad", 900, 520, 1300),
+]
+
+
+@pytest.mark.parametrize("layout,M,N,K", STREAMK_SHAPES)
+def test_gemm_streamk_forced(layout, M, N, K):
+    tr = _trainer(0)
+    rng = np.random.default_rng(hash((layout, M, N, K, 5)) % (2 ** 32))
+    r = _run(tr, layout, M, N, K, rng, splits=-1)
+    assert r["err"] < TOL[0], r
+    r = _run(tr, layout, M, N, K, rng, bias=True, act=1, splits=-1)
+    assert r["err"] < TOL[0], r
+    if layout != "wgrad":
+        r = _run(tr, layout, M, N, K, rng, aux=True, row_scale=True, sumsq=True, splits=-1)
+        assert r["err"] < TOL[0] and r["sq_err"] < 2 * TOL[0], r
+
+
+def test_gemm_streamk_policy_and_determinism():
+    """The shapes the critic update runs at the benchmark batch: split-K 0 lets the policy choose (stream-K for both),
+    the result matches the forced split-K + finish path to TF32 summation-order noise, and repeated launches are
+    bit-identical (partials are added in pair order; flags are re-armed by the owner)."""
+    tr = _trainer(0)
+    for layout, M, N, K in [("fwd", 12288, 200, 6605), ("wgrad", 6605, 200, 12288)]:
+        outs = []
+        for splits in (0, 0, 0, 3):
+            rng = np.random.default_rng(99)
+            l0 = tr.launch_count
+            r = _run(tr, layout, M, N, K, rng, bias=(layout == "fwd"), act=int(layout == "fwd"), splits=splits)
+            outs.append((r, tr.launch_count - l0))
+            assert r["err"] < TOL[0], (layout, splits, r)
+        assert outs[0][1] == 1, "stream-K is one launch (no finish pass)"
+        assert outs[3][1] >= 2
+        assert np.array_equal(outs[0][0]["out"], outs[1][0]["out"]) and np.array_equal(outs[0][0]["out"], outs[2][0]["out"])

@@ -435,11 +435,27 @@ def test_stacked_real_slot_path_matches_oracle(dims, B, mode):
     # prepared variant (data-parallel overlap path): identical result
     g1 = {k: tr.get_tensor(k, "grad").copy() for k in O.CRITIC_NAMES}
     slot.copy_(xd)
-    tr.critic_prepare(slot, zd, ed)
-    s2 = tr.critic_step(slot, zd, ed, apply=False)
+    tok = tr.critic_prepare(slot, zd, ed)
+    assert tok != 0
+    s2 = tr.critic_step(slot, zd, ed, apply=False, token=tok)
     assert s2 == s
     for k in O.CRITIC_NAMES:
         assert np.array_equal(g1[k], tr.get_tensor(k, "grad")), k
+    # a token dies with the prepared activations: any other workspace user in between (here: the sampler, which
+    # overwrites the generator activations) makes the step redo the work instead of using stale x~
+    tok = tr.critic_prepare(slot, zd, ed)
+    tr.generator(torch.full_like(zd, 3.0))
+    s3 = tr.critic_step(slot, zd, ed, apply=False, token=tok)
+    assert s3 == s
+    for k in O.CRITIC_NAMES:
+        assert np.array_equal(g1[k], tr.get_tensor(k, "grad")), k
+    tokg = tr.generator_prepare(zd)
+    tr.discriminator(xd)
+    tr.generator_step(zd, apply=False, token=tokg)
+    gg = {k: tr.get_tensor(k, "grad").copy() for k in O.GEN_NAMES}
+    tr.generator_step(zd, apply=False)
+    for k in O.GEN_NAMES:
+        assert np.array_equal(gg[k], tr.get_tensor(k, "grad")), k
 
 
 @pytest.mark.parametrize("mode", [1, 0])
@@ -530,8 +546,8 @@ def test_gram_form_critic_step_grads(dims, B, mode):
     g1 = {k: tr.get_tensor(k, "grad").copy() for k in O.CRITIC_NAMES}
     slot = tr.real_slot(B)
     slot.copy_(xd)
-    tr.critic_prepare(slot, zd, ed)
-    s2 = tr.critic_step(slot, zd, ed, apply=False)
+    tok = tr.critic_prepare(slot, zd, ed)
+    s2 = tr.critic_step(slot, zd, ed, apply=False, token=tok)
     assert s2 == s
     for k in O.CRITIC_NAMES:
         assert np.array_equal(g1[k], tr.get_tensor(k, "grad")), k
@@ -639,3 +655,48 @@ def test_fused_row_chains_over_hidden_widths(hd, B, form):
     so2, go2 = O.generator_step_grads(P, z, ocfg)
     assert abs(s2["gen_loss"] - so2["gen_loss"]) <= wtol * (abs(so2["gen_loss"]) + 1e-6)
     _check_grads(tr.get_grads(O.GEN_NAMES), go2, O.GEN_NAMES, 0, B)
+
+
+@pytest.mark.parametrize("B,iters", [(130, 400), (4096, 40)])
+def test_side_operand_ring_is_race_free(B, iters):
+    """The generator-output product writes the interpolate x^ = eps x + (1 - eps) x~ as a second output, with x
+    staged through a one-box-per-warp shared-memory ring that TMA refills while the previous chunk is still being
+    processed.  Round 2 found the refill racing the reads of the previous box (a few wrong 16-byte groups in ~2e-4 of
+    the boxes, i.e. in every 6th launch at batch 130); this repeats the launch and demands the exact blend each time.
+    The slope-mask input gradient uses the same ring and is checked the same way."""
+    import ctypes as C
+    tr, cfg, ocfg, P, (x, z, eps), (xd, zd, ed) = _setup(REF, B, 10.0, 0)
+    slot = tr.real_slot(B)
+    slot.copy_(xd)
+    xcat = tr.buffer("xcat")
+    ref = None
+    for it in range(iters):
+        xcat[B:2 * B].fill_(-7.0)
+        tr.critic_prepare(slot, zd, ed)
+        xt, xh = xcat[:B], xcat[B:2 * B]
+        want = ed[:, None] * slot + (1 - ed[:, None]) * xt
+        assert (xh - want).abs().max().item() <= 2e-7, it
+        if ref is None:
+            ref = xh.clone()
+        assert torch.equal(xh, ref), it
+    # slope-mask epilogue (dgrad through a LeakyReLU layer): D = (A B^T) . slope(aux), aux staged through the same ring
+    M, N, K = B, cfg.gex_size, cfg.disc_internal_size
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn((M, K), device="cuda", generator=g)
+    W = torch.randn((N, K), device="cuda", generator=g)
+    aux = torch.randn((M, tr.Gl), device="cuda", generator=g)
+    D = torch.empty((M, tr.Gl), device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    first = None
+    for it in range(iters // 4):
+        D.fill_(float("nan"))
+        rc = tr.lib.wgan_gemm(tr._h, 0, 0, p(A), K, p(W), K, p(D), tr.Gl, M, N, K, None, 0, p(aux), tr.Gl, None, None,
+                              None, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, tr.lib.wgan_last_error(tr._h)
+        out = D[:, :N]
+        if first is None:
+            first = out.clone()
+            raw = A.double() @ W.double().T
+            want = raw * torch.where(aux[:, :N] > 0, 1.0, cfg.alpha)
+            assert ((out.double() - want).abs().max() / want.abs().max()).item() < 2e-3
+        assert torch.equal(out, first), it
