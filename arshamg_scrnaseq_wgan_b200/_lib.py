@@ -113,7 +113,7 @@ def load() -> C.CDLL:
 
 
 DP_MAX_WORLD = 16          # WGAN_DP_MAX_WORLD
-DP_BLOB_BYTES = 128        # WGAN_DP_BLOB_BYTES
+DP_BLOB_BYTES = 192        # WGAN_DP_BLOB_BYTES
 
 
 class WganError(RuntimeError):

@@ -9,26 +9,49 @@ Logging mirrors the reference's scalar summaries loss/gen and loss/disc [W:145-1
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .trainer import PARAM_NAMES, NET_GENERATOR, NET_CRITIC
 
 
-def save_checkpoint(trainer, path: str, global_step: int = 0) -> None:
-    out = {"global_step": np.int64(global_step)}
-    for k in PARAM_NAMES:
-        out[k] = trainer.get_tensor(k, "param")
-        out[k + "/Adam"] = trainer.get_tensor(k, "m")
-        out[k + "/Adam_1"] = trainer.get_tensor(k, "v")
-    for net, scope in ((NET_GENERATOR, "generator_opt"), (NET_CRITIC, "critic_opt")):
-        b1, b2 = trainer.adam_powers(net)
-        out[scope + "/beta1_power"] = np.float32(b1)
-        out[scope + "/beta2_power"] = np.float32(b2)
-    np.savez(path, **out)
+def _npz_path(path: str) -> str:
+    return path if path.endswith(".npz") else path + ".npz"
+
+
+def save_checkpoint(trainer, path: str, global_step: int = 0, step_suffix: bool = False) -> str:
+    """Write the state dump.  Data-parallel replicas are bit-identical, so only rank 0 writes (followed by a barrier
+    when torch.distributed is up).  The file is written next to its destination and renamed into place, so a crash
+    during a save never destroys the previous checkpoint; `step_suffix` appends -<global_step> like the
+    reference's Saver [W:203].  Returns the path written (".npz" is appended when missing, for save AND load)."""
+    dest = _npz_path(path)
+    if step_suffix:
+        dest = dest[:-4] + f"-{int(global_step)}.npz"
+    if getattr(trainer, "rank", 0) == 0:
+        out = {"global_step": np.int64(global_step)}
+        for k in PARAM_NAMES:
+            out[k] = trainer.get_tensor(k, "param")
+            out[k + "/Adam"] = trainer.get_tensor(k, "m")
+            out[k + "/Adam_1"] = trainer.get_tensor(k, "v")
+        for net, scope in ((NET_GENERATOR, "generator_opt"), (NET_CRITIC, "critic_opt")):
+            b1, b2 = trainer.adam_powers(net)
+            out[scope + "/beta1_power"] = np.float32(b1)
+            out[scope + "/beta2_power"] = np.float32(b2)
+        tmp = dest + f".tmp{os.getpid()}"
+        with open(tmp, "wb") as f:
+            np.savez(f, **out)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, dest)
+    dist = getattr(trainer, "dist", None)
+    if getattr(trainer, "world", 1) > 1 and dist is not None and dist.is_available() and dist.is_initialized():
+        dist.barrier(group=getattr(trainer, "group", None))
+    return dest
 
 
 def load_checkpoint(trainer, path: str) -> int:
-    ck = np.load(path)
+    ck = np.load(path if os.path.exists(path) else _npz_path(path))
     for k in PARAM_NAMES:
         trainer.set_tensor(k, ck[k], "param")
         trainer.set_tensor(k, ck[k + "/Adam"], "m")

@@ -99,8 +99,10 @@ struct wgan_handle {
   int max_clusters[4][5];
   // data-parallel window: both gradient arenas + the cross-GPU flags in ONE allocation that peers map
   // (cudaIpc handle or, inside one process, the pointer itself); see dp_allreduce_kernel in kernels.cuh
-  float* dp_win; size_t dp_win_bytes; size_t dp_grad_off[2]; size_t dp_flags_off;
+  float* dp_win; size_t dp_win_bytes; size_t dp_grad_off[2]; size_t dp_flags_off;   // offsets in floats
+  size_t dp_stage_off, dp_stage_stride;    // staging rows [dp_world][dp_stage_stride]: peers push their contributions here
   int dp_rank, dp_world, dp_blocks; bool dp_connected;
+  bool dp_early_trigger;                   // every rank has its own GPU (wgan_dp_connect): see dp_allreduce_kernel
   float* dp_peer[WGAN_DP_MAX_WORLD];       // window base of every rank as mapped here (own rank: dp_win)
   bool dp_peer_ipc[WGAN_DP_MAX_WORLD];     // opened with cudaIpcOpenMemHandle (closed in wgan_destroy)
 
@@ -806,7 +808,8 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->dp_win = nullptr; h->dp_win_bytes = 0; h->dp_connected = false;
   h->dp_world = cfg->dp_world > 1 ? cfg->dp_world : 1;
   h->dp_rank = cfg->dp_world > 1 ? cfg->dp_rank : 0;
-  h->dp_blocks = 32;
+  h->dp_blocks = 0;                          // 0 = one block per SM (set after the device query)
+  h->dp_early_trigger = false;
   if (const char* env = getenv("WGAN_B200_DP_BLOCKS")) {
     const int b = atoi(env);
     if (b >= 1 && b <= DP_MAX_BLOCKS) h->dp_blocks = b;
@@ -850,6 +853,7 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   if (prop.major != 10) return fail("this library is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
   h->num_sms = prop.multiProcessorCount;
   h->sm_cap = h->num_sms;
+  if (h->dp_blocks == 0) h->dp_blocks = h->num_sms < DP_MAX_BLOCKS ? h->num_sms : DP_MAX_BLOCKS;
   if (h->prepare_reserve > h->num_sms / 2) h->prepare_reserve = h->num_sms / 2;
 
   void* fn = nullptr;
@@ -891,7 +895,12 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   for (int n = 0; n < 2; ++n) h->arena_n[n] = off[n] + 4;
   h->dp_grad_off[WGAN_NET_CRITIC] = 0;
   h->dp_grad_off[WGAN_NET_GENERATOR] = round64(h->arena_n[WGAN_NET_CRITIC]);
-  h->dp_flags_off = h->dp_grad_off[WGAN_NET_GENERATOR] + round64(h->arena_n[WGAN_NET_GENERATOR]);
+  h->dp_stage_off = h->dp_grad_off[WGAN_NET_GENERATOR] + round64(h->arena_n[WGAN_NET_GENERATOR]);
+  {
+    const size_t big = h->arena_n[0] > h->arena_n[1] ? h->arena_n[0] : h->arena_n[1];
+    h->dp_stage_stride = h->dp_world > 1 ? round64(big / h->dp_world + 8) : 0;   // >= the largest slice
+  }
+  h->dp_flags_off = h->dp_stage_off + static_cast<size_t>(h->dp_world > 1 ? h->dp_world : 0) * h->dp_stage_stride;
   h->dp_win_bytes = (h->dp_flags_off + DP_FLAG_WORDS) * 4;
   if (cudaMalloc(&h->dp_win, h->dp_win_bytes) != cudaSuccess) return fail("cudaMalloc(gradient window) failed");
   cudaMemset(h->dp_win, 0, h->dp_win_bytes);
@@ -1338,6 +1347,7 @@ struct DpBlob {                      // WGAN_DP_BLOB_BYTES, opaque to the caller
   int32_t blocks;
   int32_t pad;
   cudaIpcMemHandle_t ipc;            // 64 bytes
+  char uuid[16];                     // physical GPU of the exporting handle
 };
 static_assert(sizeof(DpBlob) <= WGAN_DP_BLOB_BYTES, "DpBlob must fit the rendezvous blob");
 static_assert(DP_MAX_WORLD == WGAN_DP_MAX_WORLD, "kernel and ABI disagree on the maximum group size");
@@ -1356,6 +1366,11 @@ int wgan_dp_export(wgan_handle* h, void* blob_out) {
   b.win_bytes = h->dp_win_bytes;
   b.arena_n[0] = h->arena_n[0]; b.arena_n[1] = h->arena_n[1];
   b.blocks = h->dp_blocks;
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+    memcpy(b.uuid, prop.uuid.bytes, 16);
+  }
   CK(cudaIpcGetMemHandle(&b.ipc, h->dp_win));
   memset(blob_out, 0, WGAN_DP_BLOB_BYTES);
   memcpy(blob_out, &b, sizeof b);
@@ -1369,6 +1384,15 @@ int wgan_dp_connect(wgan_handle* h, const void* blobs) {
   if (h->dp_connected) FAIL("dp_connect: already connected");
   CK(cudaSetDevice(h->cfg.device));
   const int64_t me = static_cast<int64_t>(getpid());
+  bool shared_gpu = false;
+  for (int r = 0; r < h->dp_world; ++r)
+    for (int q = 0; q < r; ++q) {
+      DpBlob a, c;
+      memcpy(&a, static_cast<const char*>(blobs) + static_cast<size_t>(r) * WGAN_DP_BLOB_BYTES, sizeof a);
+      memcpy(&c, static_cast<const char*>(blobs) + static_cast<size_t>(q) * WGAN_DP_BLOB_BYTES, sizeof c);
+      if (memcmp(a.uuid, c.uuid, 16) == 0) shared_gpu = true;
+    }
+  h->dp_early_trigger = !shared_gpu && getenv("WGAN_B200_DP_NO_EARLY") == nullptr;
   for (int r = 0; r < h->dp_world; ++r) {
     DpBlob b;
     memcpy(&b, static_cast<const char*>(blobs) + static_cast<size_t>(r) * WGAN_DP_BLOB_BYTES, sizeof b);
@@ -1412,8 +1436,11 @@ int wgan_allreduce_grads(wgan_handle* h, int net, wgan_stream_t stream) {
   p.rank = h->dp_rank; p.world = h->dp_world;
   p.grad_off = h->dp_grad_off[net];
   p.flags_off = h->dp_flags_off;
+  p.stage_off = h->dp_stage_off;
+  p.stage_stride = h->dp_stage_stride;
   p.n4 = h->arena_n[net] / 4;
-  KLAUNCH(dp_allreduce_kernel, h->dp_blocks, 512, 0, static_cast<cudaStream_t>(stream), p);
+  p.early_trigger = h->dp_early_trigger ? 1 : 0;
+  KLAUNCH(dp_allreduce_kernel, h->dp_blocks, DP_THREADS, 0, static_cast<cudaStream_t>(stream), p);
   return post_launch(h, "dp_allreduce_kernel");
 }
 

@@ -786,26 +786,32 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __r
 // ---------------------------------------------------------------------------------------------
 // Data-parallel gradient exchange over NVLink peer memory: in-place SUM over `world` ranks of one
 // gradient arena (+ the loss scalars in its tail), one launch per rank, no NCCL.
-// Every rank maps every rank's window (gradient arenas + flags, one allocation).  Two-shot: rank r owns slice r of
-// the arena; block b of rank r
-//   1. tells every peer "my gradients are final" (arrive1[b][r] = epoch) and waits for the same from every peer,
-//   2. PULLS its part of slice r from every rank, adds the W values in rank order (so every replica ends up with
-//      bit-identical sums) and PUSHES the sum into every rank's arena,
-//   3. tells every peer "my pushes are out" (arrive2[b][r] = epoch) and waits for every peer's block b.
-// When all blocks of a rank have left step 3, all slices of its arena hold the global sum and nobody reads its
-// arena any more.  The epoch lives in the window (advanced by the kernel), so a CUDA-graph replay works.
-// Flags are system-scope release/acquire; gradient values cross NVLink as 16-byte relaxed.sys accesses.
+// Every rank maps every rank's window (gradient arenas + staging + flags, one allocation).  All traffic that
+// crosses NVLink is POSTED WRITES (a pull design measured ~135 GB/s: 16-byte loads over NVLink are round trips).
+// Rank r owns slice r of the arena; block b of rank r
+//   1. pushes its part of every foreign slice k of its own arena into rank k's staging row r,
+//   2. tells every peer "my contributions have landed" (arrive1[b][r] = epoch) and waits for the same from all,
+//   3. adds, in rank order, the W contributions to its part of slice r (own arena + staging rows: local reads; every
+//      replica therefore ends up with bit-identical sums) and pushes the sum into every rank's arena,
+//   4. tells every peer "my sums have landed" (arrive2[b][r] = epoch) and waits for every peer's block b.
+// When all blocks of a rank have left step 4 its whole arena holds the global sum and nobody writes to its
+// window any more.  The epoch lives in the window (advanced by the kernel), so a CUDA-graph replay works.
+// Flags are system-scope release/acquire; gradient values move as 16-byte relaxed.sys accesses.
 // ---------------------------------------------------------------------------------------------
 constexpr int DP_MAX_WORLD = 16;
-constexpr int DP_MAX_BLOCKS = 64;
+constexpr int DP_MAX_BLOCKS = 148;
+constexpr int DP_THREADS = 256;
 constexpr int DP_FLAG_WORDS = DP_MAX_BLOCKS * (2 * DP_MAX_WORLD + 1);   // arrive1, arrive2 [block][rank]; epoch[block]
 
 struct DpParams {
   float* peer[DP_MAX_WORLD];     // window base of every rank, as mapped in this process
   int rank, world;
   size_t grad_off;               // floats from the window base to this net's gradient arena
+  size_t stage_off;              // floats from the window base to the staging rows [world][stage_stride]
+  size_t stage_stride;           // floats per staging row (>= the largest slice)
   size_t flags_off;              // floats from the window base to the flag words
   size_t n4;                     // float4 groups in the arena (scalar tail included)
+  int early_trigger;             // 1: release the next kernel's launch at once (one rank per GPU)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -816,15 +822,29 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float4* p) {
+// Gradient values: the staging rows are written by peers into THIS GPU's memory (home L2), so an L2 load (ld.cg)
+// after the acquire sees them; pushes are plain 16-byte stores that the release + system fence of the rendezvous
+// orders (WGAN_DP_SYS_ACCESS=1 builds use relaxed.sys accesses instead: measured slower, same results).
+#ifndef WGAN_DP_SYS_ACCESS
+#define WGAN_DP_SYS_ACCESS 0
+#endif
+__device__ __forceinline__ float4 dp_load_v4(const float4* p) {
+#if WGAN_DP_SYS_ACCESS
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
+#else
+  return __ldcg(p);
+#endif
 }
-__device__ __forceinline__ void st_relaxed_sys_v4(float4* p, float4 v) {
+__device__ __forceinline__ void dp_store_v4(float4* p, float4 v) {
+#if WGAN_DP_SYS_ACCESS
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
                ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+  *p = v;
+#endif
 }
 
 // One cross-GPU rendezvous of block b: publish `epoch` in slot [b][rank] of every rank's `which` array (0 =
@@ -842,11 +862,23 @@ __device__ __forceinline__ void dp_rendezvous(const DpParams& p, int which, unsi
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(512)
+// this block's share [b0, b1) of the float4 range [lo, hi)
+__device__ __forceinline__ void dp_block_part(size_t lo, size_t hi, size_t& b0, size_t& b1) {
+  const size_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
+  b0 = lo + per * blockIdx.x;
+  if (b0 > hi) b0 = hi;
+  b1 = b0 + per < hi ? b0 + per : hi;
+}
+
+// Small footprint on purpose (256 threads, <= 40 registers, no dynamic shared memory): a block fits on an SM next to a
+// persistent GEMM CTA (168 registers x 320 threads, ~200 KB of shared memory), so the exchange of update k really
+// runs beside the generator forward of update k + 1 instead of taking SMs away from it.
+__global__ void __launch_bounds__(DP_THREADS, 6)
 dp_allreduce_kernel(const DpParams p) {
-  // no early griddepcontrol.launch_dependents: blocks of the next kernel parked on the SMs could keep a PEER's
-  // all-reduce blocks (same GPU, other stream: several handles on one device) from becoming resident while this
-  // grid spins on them
+  // early_trigger = 0 (several ranks on one GPU: tests): no griddepcontrol.launch_dependents before the end --
+  // blocks of the next kernel parked on the SMs could keep a PEER's blocks (same GPU, other stream) from becoming
+  // resident while this grid spins on them.  One rank per GPU: trigger at once, the successor's launch is hidden.
+  if (p.early_trigger) pdl_launch_dependents();
   pdl_wait();
   __shared__ unsigned int s_epoch;
   unsigned int* my_flags = reinterpret_cast<unsigned int*>(p.peer[p.rank] + p.flags_off);
@@ -854,28 +886,44 @@ dp_allreduce_kernel(const DpParams p) {
   if (threadIdx.x == 0) s_epoch = *epoch_word + 1u;
   __syncthreads();
   const unsigned int epoch = s_epoch;
-  const int W = p.world;
+  const int W = p.world, R = p.rank;
+  float4* mine = reinterpret_cast<float4*>(p.peer[R] + p.grad_off);
+  // 1. scatter: my contribution to every foreign slice -> its owner's staging row R
+  for (int dk = 1; dk < W; ++dk) {
+    const int k = (R + dk) % W;                    // start with the next rank: spreads the first writes over the links
+    const size_t lo = p.n4 * k / W, hi = p.n4 * (k + 1) / W;
+    size_t b0, b1;
+    dp_block_part(lo, hi, b0, b1);
+    float4* dst = reinterpret_cast<float4*>(p.peer[k] + p.stage_off + static_cast<size_t>(R) * p.stage_stride) - lo;
+    size_t i = b0 + threadIdx.x;
+    for (; i + DP_THREADS < b1; i += 2 * DP_THREADS) {
+      const float4 v0 = mine[i], v1 = mine[i + DP_THREADS];
+      dp_store_v4(dst + i, v0); dp_store_v4(dst + i + DP_THREADS, v1);
+    }
+    if (i < b1) dp_store_v4(dst + i, mine[i]);
+  }
   dp_rendezvous(p, 0, epoch);
-  // this block's part of slice `rank`
-  const size_t lo = p.n4 * p.rank / W, hi = p.n4 * (p.rank + 1) / W;
-  const size_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
-  const size_t b0 = lo + per * blockIdx.x, b1 = b0 + per < hi ? b0 + per : hi;
-  for (size_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
-    float4 v[DP_MAX_WORLD];
-#pragma unroll
-    for (int k = 0; k < DP_MAX_WORLD; ++k)
-      if (k < W) v[k] = ld_relaxed_sys_v4(reinterpret_cast<const float4*>(p.peer[k] + p.grad_off) + i);
-    float4 acc = v[0];
-#pragma unroll
-    for (int k = 1; k < DP_MAX_WORLD; ++k)
-      if (k < W) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
-#pragma unroll
-    for (int k = 0; k < DP_MAX_WORLD; ++k)
-      if (k < W) st_relaxed_sys_v4(reinterpret_cast<float4*>(p.peer[k] + p.grad_off) + i, acc);
+  // 3. reduce my part of slice R in rank order, broadcast the sum
+  {
+    const size_t lo = p.n4 * R / W, hi = p.n4 * (R + 1) / W;
+    size_t b0, b1;
+    dp_block_part(lo, hi, b0, b1);
+    const float4* stage = reinterpret_cast<const float4*>(p.peer[R] + p.stage_off) - lo;
+    const size_t row4 = p.stage_stride / 4;
+    for (size_t i = b0 + threadIdx.x; i < b1; i += DP_THREADS) {
+      float4 acc = (R == 0) ? mine[i] : dp_load_v4(stage + i);
+      for (int k = 1; k < W; ++k) {
+        const float4 v = (k == R) ? mine[i] : dp_load_v4(stage + static_cast<size_t>(k) * row4 + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      mine[i] = acc;
+      for (int dk = 1; dk < W; ++dk)
+        dp_store_v4(reinterpret_cast<float4*>(p.peer[(R + dk) % W] + p.grad_off) + i, acc);
+    }
   }
   dp_rendezvous(p, 1, epoch);
   if (threadIdx.x == 0) *epoch_word = epoch;
-  pdl_launch_dependents();
+  if (!p.early_trigger) pdl_launch_dependents();
 }
 
 // Latent fit (build-defined): r = G(z) - x; loss[b] = sum r^2; d3 = 2 r slope(G(z)).

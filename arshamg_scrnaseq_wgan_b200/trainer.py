@@ -83,8 +83,24 @@ class _DevPtr:
                                          "version": 2}
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+class _OnDevice:
+    """The handle-less input-pipeline entry points launch on the CURRENT CUDA device; this proxy makes the
+    trainer's device current around each call (two trainers on different GPUs in one process)."""
+
+    def __init__(self, lib, device):
+        self._lib, self._device = lib, device
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+
+        def call(*a):
+            with torch.cuda.device(self._device):
+                return fn(*a)
+        return call
+
+
+def _stream(device=None) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class WGANTrainer:
@@ -141,6 +157,7 @@ class WGANTrainer:
             self.info[ti.name.decode()] = (i, ti.net, ti.rows, ti.cols, ti.ld, ti.offset)
         self.Gl = self.lib.wgan_padded_ld(cfg.gex_size)
         self._grad_arena = {n: self.arena(n, KIND_GRAD) for n in (NET_GENERATOR, NET_CRITIC)}
+        self._pl = _OnDevice(self.lib, self.device)
         self._data = None
         self._data_max_value = 1.0
         self._calls = 0
@@ -150,6 +167,10 @@ class WGANTrainer:
             self._dp_connect_distributed()
 
     # ------------------------------------------------------------------ plumbing
+    def _st(self) -> C.c_void_p:
+        """torch's current stream ON THIS TRAINER'S GPU (not the process-wide current device)."""
+        return _stream(self.device)
+
     def _ck(self, rc, what):
         _lib.check(self.lib, self._h, rc, what)
 
@@ -286,13 +307,13 @@ class WGANTrainer:
             return
         assert self._dp_connected, "data-parallel trainer: call dp_connect(blobs) before the first step"
         if overlap is None or os.environ.get("WGAN_B200_DP_SERIAL"):
-            self._ck(self.lib.wgan_allreduce_grads(self._h, net, _stream()), "allreduce_grads")
+            self._ck(self.lib.wgan_allreduce_grads(self._h, net, self._st()), "allreduce_grads")
             if overlap is not None:
                 overlap()
             return
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=f"cuda:{self.device}", priority=-1)
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.device)
         self._comm_stream.wait_stream(main)
         self._ck(self.lib.wgan_allreduce_grads(self._h, net, C.c_void_p(self._comm_stream.cuda_stream)),
                  "allreduce_grads")
@@ -306,20 +327,20 @@ class WGANTrainer:
         zp, ldz, _ = self._mat(z, self.cfg.noise_input_size)
         ep = C.c_void_p(eps.data_ptr()) if eps is not None else C.c_void_p()
         tok = C.c_uint64(0)
-        self._ck(self.lib.wgan_critic_prepare(self._h, xp, ldx, zp, ldz, ep, rows, _stream(), C.byref(tok)),
+        self._ck(self.lib.wgan_critic_prepare(self._h, xp, ldx, zp, ldz, ep, rows, self._st(), C.byref(tok)),
                  "critic_prepare")
         return tok.value
 
     def scalars(self, net: int) -> np.ndarray:
         out = np.empty(4, np.float32)
-        self._ck(self.lib.wgan_get_scalars(self._h, net, out.ctypes.data_as(C.c_void_p), _stream()), "get_scalars")
+        self._ck(self.lib.wgan_get_scalars(self._h, net, out.ctypes.data_as(C.c_void_p), self._st()), "get_scalars")
         return out
 
     def generator_prepare(self, z) -> int:
         """Run the critic-independent part (z staging, G(z)) of the next generator_step(z) now."""
         zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
         tok = C.c_uint64(0)
-        self._ck(self.lib.wgan_generator_prepare(self._h, zp, ldz, rows, _stream(), C.byref(tok)), "generator_prepare")
+        self._ck(self.lib.wgan_generator_prepare(self._h, zp, ldz, rows, self._st(), C.byref(tok)), "generator_prepare")
         return tok.value
 
     def critic_step(self, x, z, eps=None, apply: bool = True, read: bool = True, global_batch: Optional[int] = None,
@@ -334,11 +355,11 @@ class WGANTrainer:
         if eps is not None:
             assert eps.is_cuda and eps.dtype == torch.float32 and eps.numel() == rows and eps.is_contiguous()
         gb = rows * self.world if global_batch is None else int(global_batch)
-        self._ck(self.lib.wgan_critic_grads(self._h, xp, ldx, zp, ldz, ep, rows, gb, int(token or 0), _stream()),
+        self._ck(self.lib.wgan_critic_grads(self._h, xp, ldx, zp, ldz, ep, rows, gb, int(token or 0), self._st()),
                  "critic_grads")
         self._allreduce(NET_CRITIC, overlap)
         if apply:
-            self._ck(self.lib.wgan_critic_apply(self._h, _stream()), "critic_apply")
+            self._ck(self.lib.wgan_critic_apply(self._h, self._st()), "critic_apply")
         if not read:
             return None
         s = self.scalars(NET_CRITIC)
@@ -350,11 +371,11 @@ class WGANTrainer:
         """One generator update [W:196]: gradients of obj_g through the critic, all-reduce, Adam."""
         zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
         gb = rows * self.world if global_batch is None else int(global_batch)
-        self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, gb, int(token or 0), _stream()),
+        self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, gb, int(token or 0), self._st()),
                  "generator_grads")
         self._allreduce(NET_GENERATOR)
         if apply:
-            self._ck(self.lib.wgan_generator_apply(self._h, _stream()), "generator_apply")
+            self._ck(self.lib.wgan_generator_apply(self._h, self._st()), "generator_apply")
         if not read:
             return None
         return {"gen_loss": -float(self.scalars(NET_GENERATOR)[0])}     # obj_g [W:138]
@@ -374,20 +395,22 @@ class WGANTrainer:
             out = torch.empty((rows, self.Gl), device=z.device, dtype=torch.float32)[:, :self.cfg.gex_size]
         op, ldo, ro = self._mat(out, self.cfg.gex_size)
         assert ro == rows
-        self._ck(self.lib.wgan_sample(self._h, zp, ldz, op, ldo, rows, _stream()), "sample")
+        self._ck(self.lib.wgan_sample(self._h, zp, ldz, op, ldo, rows, self._st()), "sample")
         return out
 
     def discriminator(self, x) -> torch.Tensor:
         """D(x) [W:103-124]: [rows, gex] -> [rows, 1] (linear output, no sigmoid)."""
         xp, ldx, rows = self._mat(x, self.cfg.gex_size)
         out = torch.empty((rows, 1), device=x.device, dtype=torch.float32)
-        self._ck(self.lib.wgan_critic_forward(self._h, xp, ldx, C.c_void_p(out.data_ptr()), rows, _stream()),
+        self._ck(self.lib.wgan_critic_forward(self._h, xp, ldx, C.c_void_p(out.data_ptr()), rows, self._st()),
                  "critic_forward")
         return out
 
     def noise_prior(self, batch_size: int, dim: Optional[int] = None, seed: int = 0, call_id: Optional[int] = None,
-                    row0: Optional[int] = None, data_max_value: float = 1.0, counter=None) -> torch.Tensor:
-        """abs(Normal(0, data_max/10) + Poisson(1)) [W:91-94], drawn on the device (Philox)."""
+                    row0: Optional[int] = None, data_max_value: Optional[float] = None, counter=None) -> torch.Tensor:
+        """abs(Normal(0, data_max/10) + Poisson(1)) [W:91-94], drawn on the device (Philox).  data_max_value defaults
+        to the maximum of the resident training matrix (set_data), 1.0 before any data is set."""
+        data_max_value = self._data_max_value if data_max_value is None else data_max_value
         dim = self.cfg.noise_input_size if dim is None else dim
         if call_id is None:
             call_id = self._calls
@@ -395,8 +418,8 @@ class WGANTrainer:
         if row0 is None:
             row0 = self.rank * batch_size
         out = torch.empty((batch_size, dim), device=f"cuda:{self.device}", dtype=torch.float32)
-        rc = self.lib.wgan_rng_noise_prior(C.c_void_p(out.data_ptr()), dim, row0, batch_size, dim,
-                                           data_max_value / 10.0, seed, call_id, self._cptr(counter), _stream())
+        rc = self._pl.wgan_rng_noise_prior(C.c_void_p(out.data_ptr()), dim, row0, batch_size, dim,
+                                           data_max_value / 10.0, seed, call_id, self._cptr(counter), self._st())
         if rc != 0:
             raise _lib.WganError("rng_noise_prior: " + self.lib.wgan_last_error(None).decode())
         return out
@@ -408,8 +431,8 @@ class WGANTrainer:
     def uniform(self, rows: int, seed: int, call_id: int, row0: Optional[int] = None, counter=None) -> torch.Tensor:
         out = torch.empty((rows,), device=f"cuda:{self.device}", dtype=torch.float32)
         row0 = self.rank * rows if row0 is None else row0
-        rc = self.lib.wgan_rng_uniform(C.c_void_p(out.data_ptr()), row0, rows, seed, call_id, self._cptr(counter),
-                                       _stream())
+        rc = self._pl.wgan_rng_uniform(C.c_void_p(out.data_ptr()), row0, rows, seed, call_id, self._cptr(counter),
+                                       self._st())
         if rc != 0:
             raise _lib.WganError("rng_uniform: " + self.lib.wgan_last_error(None).decode())
         return out
@@ -418,21 +441,24 @@ class WGANTrainer:
                 counter=None) -> torch.Tensor:
         out = torch.empty((rows,), device=f"cuda:{self.device}", dtype=torch.int64)
         row0 = self.rank * rows if row0 is None else row0
-        rc = self.lib.wgan_rng_indices(C.c_void_p(out.data_ptr()), row0, rows, n_cells, seed, call_id,
-                                       self._cptr(counter), _stream())
+        rc = self._pl.wgan_rng_indices(C.c_void_p(out.data_ptr()), row0, rows, n_cells, seed, call_id,
+                                       self._cptr(counter), self._st())
         if rc != 0:
             raise _lib.WganError("rng_indices: " + self.lib.wgan_last_error(None).decode())
         return out
 
     # ------------------------------------------------------------------ resident-data training
-    def set_data(self, cells_by_genes: torch.Tensor):
+    def set_data(self, cells_by_genes: torch.Tensor, data_max_value: Optional[float] = None):
         """Keep the (already min-max scaled) training matrix resident, cells-major, padded rows
-        (the reference keeps it genes-major on the host and gathers columns every step [W:188-191])."""
+        (the reference keeps it genes-major on the host and gathers columns every step [W:188-191]).
+        `data_max_value` = np.amax(training matrix) [W:89] (what prepare_training_matrix returns; computed here when
+        omitted): the noise prior of every resident / graph / sampling path uses sigma = data_max_value / 10 [W:93]."""
         n, g = cells_by_genes.shape
         assert g == self.cfg.gex_size
         buf = torch.zeros((n, self.Gl), device=f"cuda:{self.device}", dtype=torch.float32)
         buf[:, :g] = cells_by_genes.to(buf.device, torch.float32)
         self._data = buf
+        self._data_max_value = float(buf.max().item()) if data_max_value is None else float(data_max_value)
 
     def real_slot(self, rows: int) -> torch.Tensor:
         """The rows of the library's stacked activation buffer ([fake | interpolate | real], or
@@ -446,24 +472,25 @@ class WGANTrainer:
     def gather(self, idx: torch.Tensor) -> torch.Tensor:
         rows = idx.numel()
         out = self.real_slot(rows)
-        rc = self.lib.wgan_gather_rows(C.c_void_p(self._data.data_ptr()), self.Gl, C.c_void_p(idx.data_ptr()),
-                                       C.c_void_p(out.data_ptr()), self.Gl, rows, self.cfg.gex_size, _stream())
+        rc = self._pl.wgan_gather_rows(C.c_void_p(self._data.data_ptr()), self.Gl, C.c_void_p(idx.data_ptr()),
+                                       C.c_void_p(out.data_ptr()), self.Gl, rows, self.cfg.gex_size, self._st())
         if rc != 0:
             raise _lib.WganError("gather_rows: " + self.lib.wgan_last_error(None).decode())
         return out
 
-    def draw_minibatch(self, batch: int, seed: int, call_id: int, counter=None, data_max_value: float = 1.0):
+    def draw_minibatch(self, batch: int, seed: int, call_id: int, counter=None, data_max_value: Optional[float] = None):
         """Indices [W:188] + gather [W:189-191] + noise [W:193] + epsilon of one critic update in a single
         launch; the same values as indices() / gather() / noise_prior() / uniform() with this call id."""
         dev = f"cuda:{self.device}"
+        data_max_value = self._data_max_value if data_max_value is None else data_max_value
         x = self.real_slot(batch)
         z = torch.empty((batch, self.cfg.noise_input_size), device=dev, dtype=torch.float32)
         eps = torch.empty((batch,), device=dev, dtype=torch.float32) if self.cfg.lambda_gp != 0 else None
-        rc = self.lib.wgan_draw_minibatch(
+        rc = self._pl.wgan_draw_minibatch(
             C.c_void_p(self._data.data_ptr()), self.Gl, self._data.shape[0], C.c_void_p(x.data_ptr()), self.Gl,
             self.cfg.gex_size, C.c_void_p(z.data_ptr()), z.shape[1], z.shape[1], data_max_value / 10.0,
             C.c_void_p(eps.data_ptr()) if eps is not None else C.c_void_p(), C.c_void_p(), self.rank * batch, batch,
-            seed, call_id, self._cptr(counter), _stream())
+            seed, call_id, self._cptr(counter), self._st())
         if rc != 0:
             raise _lib.WganError("draw_minibatch: " + self.lib.wgan_last_error(None).decode())
         return x, z, eps
@@ -483,7 +510,8 @@ class WGANTrainer:
         def draw(k):
             if os.environ.get("WGAN_B200_SPLIT_DRAW"):          # experiment: the four separate launches
                 cid = base + k
-                z = self.noise_prior(batch, seed=seed, call_id=cid, counter=counter)
+                z = self.noise_prior(batch, seed=seed, call_id=cid, counter=counter,
+                                     data_max_value=self._data_max_value)
                 x = self.gather(self.indices(batch, self._data.shape[0], seed, cid, counter=counter))
                 eps = self.uniform(batch, seed, cid, counter=counter) if cfg.lambda_gp != 0 else None
                 return x, z, eps
@@ -530,17 +558,17 @@ class WGANTrainer:
         counter = torch.full((1,), start_it * (cfg.n_critic + 1), dtype=torch.int32, device=f"cuda:{self.device}")
         # warm-up outside capture (lazy attribute / occupancy queries, NCCL communicators), then rewind
         side = torch.cuda.Stream(device=f"cuda:{self.device}")
-        side.wait_stream(torch.cuda.current_stream())
+        side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             self.train_iteration_resident(0, batch, seed=seed, counter=counter)
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream(self.device).wait_stream(side)
         counter += cfg.n_critic + 1            # the eager warm-up WAS iteration start_it; replays continue from there
         torch.cuda.synchronize()
         l0 = self.launch_count
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self.train_iteration_resident(0, batch, seed=seed, counter=counter)
-            rc = self.lib.wgan_counter_add(C.c_void_p(counter.data_ptr()), cfg.n_critic + 1, _stream())
+            rc = self._pl.wgan_counter_add(C.c_void_p(counter.data_ptr()), cfg.n_critic + 1, self._st())
             if rc != 0:
                 raise _lib.WganError("counter_add: " + self.lib.wgan_last_error(None).decode())
         self._graph_keepalive = (graph, counter)
@@ -602,7 +630,8 @@ class WGANTrainer:
         buf = None if sink is None else torch.empty((chunk, self.Gl), device=f"cuda:{self.device}", dtype=torch.float32)
         for r0 in range(0, n_cells, chunk):
             n = min(chunk, n_cells - r0)
-            z = self.noise_prior(n, seed=seed, call_id=0x5A3D0000, row0=base + r0)
+            z = self.noise_prior(n, seed=seed, call_id=0x5A3D0000, row0=base + r0,
+                                 data_max_value=self._data_max_value)
             dst = (out[r0:r0 + n] if sink is None else buf[:n])[:, :self.cfg.gex_size]
             self.generator(z, out=dst)
             if sink is not None:
@@ -626,8 +655,9 @@ class WGANTrainer:
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._ready = [torch.cuda.Event() for _ in range(2)]
             self._free = [torch.cuda.Event() for _ in range(2)]
+            self._zgen_free = None         # recorded after the generator step that last read _zgen
             self._nfeed = 0
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.device)
         out = {}
         n = len(xs)
         for k in range(n):
@@ -641,6 +671,10 @@ class WGANTrainer:
                 if cfg.lambda_gp != 0:
                     ed.copy_(epss[k], non_blocking=True)
                 if k == n - 1:
+                    # the previous iteration's generator step may still be reading the latent (the slot events above
+                    # only cover critic updates, which with n_critic <= 2 were recorded BEFORE that generator step)
+                    if self._zgen_free is not None:
+                        self._copy_stream.wait_event(self._zgen_free)
                     self._zgen.copy_(z_gen, non_blocking=True)
                 self._ready[slot].record(self._copy_stream)
             main.wait_event(self._ready[slot])
@@ -650,6 +684,8 @@ class WGANTrainer:
             if r:
                 out.update(r)
         r = self.generator_step(self._zgen, read=read)
+        self._zgen_free = torch.cuda.Event()
+        self._zgen_free.record(main)
         if r:
             out.update(r)
         return out if read else None
@@ -679,7 +715,7 @@ class WGANTrainer:
             def body():
                 # all host->device copies of the iteration go to a second stream (a fork inside the graph), so
                 # the feed of update k+1 overlaps the kernels of update k
-                main = torch.cuda.current_stream()
+                main = torch.cuda.current_stream(self.device)
                 copy_stream.wait_stream(main)
                 with torch.cuda.stream(copy_stream):
                     for k in range(n):
@@ -701,10 +737,10 @@ class WGANTrainer:
                 h_scal[4:8].copy_(self._grad_arena[NET_GENERATOR][-4:], non_blocking=True)
 
             side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
+            side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 body()                                   # eager warm-up (this IS a training iteration)
-            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -718,7 +754,7 @@ class WGANTrainer:
             g.replay()
         if not read:
             return None
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
         s = h_scal.numpy()
         wass = float(s[0] - s[1])
         return {"wasserstein": wass, "gp": float(s[2]), "critic_loss": wass + float(s[2]), "gen_loss": -float(s[4])}
@@ -739,8 +775,9 @@ class WGANTrainer:
             self._icopy = torch.cuda.Stream(device=dev)
             self._iready = [torch.cuda.Event() for _ in range(2)]
             self._ifree = [torch.cuda.Event() for _ in range(2)]
+            self._izgen_free = None
             self._infeed = 0
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.device)
         out = {}
         n = len(idxs)
         for k in range(n):
@@ -754,6 +791,8 @@ class WGANTrainer:
                 if cfg.lambda_gp != 0:
                     ed.copy_(epss[k], non_blocking=True)
                 if k == n - 1:
+                    if self._izgen_free is not None:       # see train_iteration_host
+                        self._icopy.wait_event(self._izgen_free)
                     self._izgen.copy_(z_gen, non_blocking=True)
                 self._iready[slot].record(self._icopy)
             main.wait_event(self._iready[slot])
@@ -764,14 +803,17 @@ class WGANTrainer:
             if r:
                 out.update(r)
         r = self.generator_step(self._izgen, read=read)
+        self._izgen_free = torch.cuda.Event()
+        self._izgen_free.record(main)
         if r:
             out.update(r)
         return out if read else None
 
     # ------------------------------------------------------------------ latent fit
     def latent_fit(self, x: torch.Tensor, steps: int, learn_rate: float = 1e-2, seed: int = 0,
-                   z0: Optional[torch.Tensor] = None):
-        """min_z sum_g (G(z) - x)^2 per cell with G frozen, TF-Adam on z.  Returns (z, loss)."""
+                   z0: Optional[torch.Tensor] = None, return_state: bool = False):
+        """min_z sum_g (G(z) - x)^2 per cell with G frozen, TF-Adam on z.  Returns (z, loss), or with
+        `return_state` (z, loss, m, v): the Adam slots of z (after one step from zero state m = (1 - beta1) dL/dz)."""
         xp, ldx, rows = self._mat(x, self.cfg.gex_size)
         Z = self.cfg.noise_input_size
         z = (z0.clone() if z0 is not None else self.noise_prior(rows, seed=seed, call_id=0x7FFF0000)).contiguous()
@@ -782,9 +824,9 @@ class WGANTrainer:
         for _ in range(steps):
             self._ck(self.lib.wgan_latent_fit_step(self._h, C.c_void_p(z.data_ptr()), C.c_void_p(m.data_ptr()),
                                                    C.c_void_p(v.data_ptr()), C.c_void_p(pw.data_ptr()), xp, ldx,
-                                                   C.c_void_p(loss.data_ptr()), rows, learn_rate, _stream()),
+                                                   C.c_void_p(loss.data_ptr()), rows, learn_rate, self._st()),
                      "latent_fit_step")
-        return z, loss
+        return (z, loss, m, v) if return_state else (z, loss)
 
 
 def generator(trainer: WGANTrainer, z, reuse: bool = False):

@@ -61,7 +61,7 @@ typedef struct wgan_config {
 /* Data-parallel rendezvous blob: opaque to the caller, produced by wgan_dp_export on every rank, gathered in rank
  * order and passed to wgan_dp_connect on every rank. */
 #define WGAN_DP_MAX_WORLD 16
-#define WGAN_DP_BLOB_BYTES 128
+#define WGAN_DP_BLOB_BYTES 192
 
 enum { WGAN_NET_GENERATOR = 0, WGAN_NET_CRITIC = 1 };
 enum { WGAN_KIND_PARAM = 0, WGAN_KIND_GRAD = 1, WGAN_KIND_M = 2, WGAN_KIND_V = 3 };

@@ -64,9 +64,3 @@ def latent_fit_grads(P, z, x, alpha=0.2):
     loss = ((_gen(gp_, z, alpha) - x) ** 2).sum(dim=1)
     (dz,) = torch.autograd.grad(loss.sum(), z)
     return loss.detach().numpy(), dz.numpy()
-
-
-def torch_reference_adam_is_not_tf_adam():
-    """Documentation hook: torch.optim.Adam uses m_hat/(sqrt(v_hat)+eps); TF puts eps outside
-    the bias correction [A:56-61].  Never validate the optimizer against torch.optim.Adam."""
-    return True

@@ -81,11 +81,16 @@ def gp_tol(mode, B):
     return max(GP_TOL[mode], (1.5 if mode == 0 else 0.02) / B)
 
 
+MEASURED_LOG = []        # (test id, mode, B, tensor, fro, fro tolerance, max_rel, max_rel tolerance): conftest dumps it
+
+
 def _check_grads(g, go, names, mode, B):
     for k in names:
         if np.abs(go[k]).max() == 0:
             assert np.abs(g[k]).max() == 0, k
             continue
+        MEASURED_LOG.append((os.environ.get("PYTEST_CURRENT_TEST", ""), mode, B, k, _fro(g[k], go[k]), fro_tol(mode, B),
+                             _relerr(g[k], go[k]), max_tol(mode, B)))
         assert _fro(g[k], go[k]) < fro_tol(mode, B), (k, _fro(g[k], go[k]), fro_tol(mode, B))
         assert _relerr(g[k], go[k]) < max_tol(mode, B), (k, _relerr(g[k], go[k]))
 
