@@ -57,6 +57,7 @@ SIGNATURES = {
     "wgan_dp_export": (_I, [_P, _P]),
     "wgan_dp_connect": (_I, [_P, _P]),
     "wgan_allreduce_grads": (_I, [_P, _I, _P]),
+    "wgan_generator_grads_exchange": (_I, [_P, _P, _I, _I, _I, C.c_uint64, _P]),
     "wgan_sample": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "wgan_critic_forward": (_I, [_P, _P, _I, _P, _I, _P]),
     "wgan_latent_fit_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _F, _P]),

@@ -371,9 +371,15 @@ class WGANTrainer:
         """One generator update [W:196]: gradients of obj_g through the critic, all-reduce, Adam."""
         zp, ldz, rows = self._mat(z, self.cfg.noise_input_size)
         gb = rows * self.world if global_batch is None else int(global_batch)
-        self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, gb, int(token or 0), self._st()),
-                 "generator_grads")
-        self._allreduce(NET_GENERATOR)
+        if self.world > 1 and self.dp_backend == "engine" and not os.environ.get("WGAN_B200_DP_SERIAL"):
+            # gradients + exchange in one call: the output layer's 16 MB go out while the backward pass continues
+            assert self._dp_connected, "data-parallel trainer: call dp_connect(blobs) before the first step"
+            self._ck(self.lib.wgan_generator_grads_exchange(self._h, zp, ldz, rows, gb, int(token or 0), self._st()),
+                     "generator_grads_exchange")
+        else:
+            self._ck(self.lib.wgan_generator_grads(self._h, zp, ldz, rows, gb, int(token or 0), self._st()),
+                     "generator_grads")
+            self._allreduce(NET_GENERATOR)
         if apply:
             self._ck(self.lib.wgan_generator_apply(self._h, self._st()), "generator_apply")
         if not read:

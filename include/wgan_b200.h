@@ -129,9 +129,10 @@ int wgan_generator_apply(wgan_handle* h, wgan_stream_t stream);
 
 /* ---- data parallelism: batch-sharded ranks, one SUM all-reduce of a net's gradient arena per optimizer step
  *      (the step it sits inside: minimize = gradients -> [all-reduce] -> apply_adam, [W:154-155],
- *      [A:140-151]).  The exchange is the engine's own kernel over NVLink peer memory (no NCCL): rank r pulls
- *      slice r of every rank's arena, adds them in rank order and pushes the sum back into every arena, so all
- *      replicas hold bit-identical gradients and stay bit-identical after Adam. ---- */
+ *      [A:140-151]).  The exchange is the engine's own kernel over NVLink peer memory (no NCCL), all cross-GPU
+ *      traffic being posted writes: every rank pushes its contribution to slice r into rank r's staging rows,
+ *      rank r adds the contributions in rank order and pushes the sum into every arena, so all replicas hold
+ *      bit-identical gradients and stay bit-identical after Adam. ---- */
 /* Writes this rank's WGAN_DP_BLOB_BYTES rendezvous blob. */
 int wgan_dp_export(wgan_handle* h, void* blob_out);
 /* blobs: dp_world * WGAN_DP_BLOB_BYTES bytes, blob of rank i at offset i * WGAN_DP_BLOB_BYTES.  Maps the peers'
@@ -141,6 +142,14 @@ int wgan_dp_connect(wgan_handle* h, const void* blobs);
 /* In-place SUM over all ranks of net's GRAD arena (incl. the WGAN_S_* scalar tail); asynchronous on `stream`,
  * collective (every rank calls it for the same net in the same order).  A no-op when dp_world <= 1. */
 int wgan_allreduce_grads(wgan_handle* h, int net, wgan_stream_t stream);
+/* wgan_generator_grads + the exchange of the generator's gradient arena in one call, overlapped: as soon as the
+ * output layer's gradients (kernel + bias, 90 % of the arena) and the loss scalar are final they are summed over the
+ * ranks on an internal high-priority stream while the rest of the backward pass [W:155] runs on `stream`; the
+ * remaining tensors follow at the end.  Same results as wgan_generator_grads followed by
+ * wgan_allreduce_grads(WGAN_NET_GENERATOR) bit for bit; collective; equal to wgan_generator_grads when
+ * dp_world <= 1.  Capturable into a CUDA graph (the internal stream forks from and joins `stream`). */
+int wgan_generator_grads_exchange(wgan_handle* h, const float* z_dev, int ldz, int rows, int global_batch,
+                                  uint64_t prepared_token, wgan_stream_t stream);
 
 /* ---- sampling: G(z) for a batch of cells (replaces the batch-1 loop [W:217-221]) ---- */
 int wgan_sample(wgan_handle* h, const float* z_dev, int ldz, float* out_dev, int ld_out, int rows,

@@ -33,6 +33,10 @@ elif which == "l1":
     A = torch.rand((3 * B, Gl), device=dev); W = torch.rand((G, Hd), device=dev) - 0.5
     bias = torch.zeros((Hd,), device=dev); D = torch.empty((3 * B, Hd), device=dev)
     fn = lambda: gemm(0, 1, A, W, D, 3 * B, Hd, G, bias, 1)
+elif which == "w1":
+    A = torch.rand((3 * B, Gl), device=dev); Dl = torch.rand((3 * B, Hd), device=dev) - 0.5
+    D = torch.empty((G, Hd), device=dev)
+    fn = lambda: gemm(1, 1, A, Dl, D, G, Hd, 3 * B)
 elif which == "dgrad2":
     A = torch.rand((3 * B, Hd), device=dev); W = torch.rand((Hd, Hd), device=dev) - 0.5
     aux = torch.rand((3 * B, Hd), device=dev) - 0.5; D = torch.empty((3 * B, Hd), device=dev)

@@ -151,6 +151,8 @@ STREAMK_SHAPES = [
     ("fwd", 256, 200, 6605), ("fwd", 300, 200, 4000), ("wgrad", 661, 200, 4096), ("dgrad", 512, 96, 3000),
     # the two layer-1 products of the critic update at batch 1024 (policy picks stream-K there, see below)
     ("fwd", 3072, 200, 6605), ("wgrad", 6605, 200, 3072),
+    # 512-row pair tiles (two sub-tiles per CTA: M >= 1024, K >= 2048, one N tile) with ragged M / N / K
+    ("fwd", 1100, 200, 2100), ("wgrad", 1500, 130, 2500), ("dgrad", 1300, 96, 3000), ("fwd", 1025, 7, 2049),
     # ragged everything, multiple N tiles, units not divisible by the pair count
     ("fwd", 1000, 700, 1111), ("dgrad", 777, 300, 2500), ("wgrad", 900, 520, 1300),
 ]

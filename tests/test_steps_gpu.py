@@ -2,15 +2,20 @@
 penalty, every parameter gradient, post-Adam parameters / m / v, sampling, RNG, multi-step drift.
 All device calls go through the C ABI (ctypes).
 
-Stated tolerances.  The network's derivative is discontinuous (LeakyReLU slope 1 vs 0.2), so any
-two finite-precision evaluations disagree on the slope of the few units whose pre-activation is
-within rounding error of zero ("mask flips"); each flip perturbs a batch-summed gradient entry by
+Stated tolerances -- every bound below is at most ~2x the worst error MEASURED on B200 for its class of case
+(profiles/r02_step_errors.json: measured value next to the bound for every test here; profiles/r02_parity_report.json:
+the per-tensor table at reference dims for B = 32 / 200 / 4096).  The network's derivative is discontinuous
+(LeakyReLU slope 1 vs 0.2), so any two finite-precision evaluations disagree on the slope of the few units whose
+pre-activation is within rounding error of zero ("mask flips"); each flip perturbs a batch-summed gradient entry by
 O(1/B) of its size.  Errors are therefore stated per tensor as relative Frobenius error
     fro = ||got - ref||_F / ||ref||_F  <=  c * sqrt(32 / B)
-with c = 2.5e-2 in TF32 tensor-core mode (10-bit-mantissa operands: pre-activation error ~5e-4
-flips ~0.1 % of the masks; measured 1.1e-3 at the benchmark batch 4096, i.e. the north-star's
-1e-3 class) and c = 2e-3 in the FP32 verification mode (measured 6e-5 at B = 4096), plus a loose
-max-normalised bound.  Scalars: Wasserstein estimate within 1e-3 (TF32) / 1e-5 (FP32) of
+with c = 2.5e-2 in TF32 tensor-core mode (10-bit-mantissa operands; measured 1.45e-2 at B = 32, 4.6e-3 at B = 200,
+1.1e-3 at the benchmark batch 4096, i.e. the north-star's 1e-3 class) and c = 1e-3 in the FP32 verification mode
+(measured <= 2.3e-4 * sqrt(32/B) on the widened nets, 1e-7 where no unit flips), plus a max-normalised entry bound
+0.45 / sqrt(B) (TF32; measured 0.335 / sqrt(B) at worst) / 7e-3 (FP32; measured 3.5e-3 on the widened nets).  Below
+16 rows a single flipped mask or a penalty norm close to 1 is a visible fraction of the whole gradient (measured
+0.19 at B = 7 in TF32 with the same case at 2e-7 in FP32): those cases check ragged-shape plumbing, the FP32 mode
+checks their arithmetic.  Scalars: Wasserstein estimate within 1e-3 (TF32) / 1e-5 (FP32) of
 |mean D_fake| + |mean D_real|; gradient penalty within 3e-2 / 1e-3 relative; per-row gradient norms
 by their median relative error (1e-3 / 1e-6) because a single flip moves one row's norm by ~1 %.
 Given identical gradients the Adam update is bit-exact.
@@ -26,8 +31,8 @@ pytestmark = pytest.mark.gpu
 
 from oracle import wgan_oracle as O  # noqa: E402
 
-FRO_C = {0: 2.5e-2, 1: 2e-3}
-MAX_TOL = {0: 8e-2, 1: 1e-2}
+FRO_C = {0: 2.5e-2, 1: 1e-3}
+MAX_TOL = {0: 0.45, 1: 7e-3}        # TF32: divided by sqrt(B)
 W_TOL = {0: 1e-3, 1: 1e-5}
 GP_TOL = {0: 3e-2, 1: 1e-3}
 NORM_MED_TOL = {0: 1e-3, 1: 1e-6}
@@ -38,8 +43,7 @@ REF = dict(noise_input_size=100, inflate_to_size=600, gex_size=6605, disc_intern
 
 def fro_tol(mode, B):
     if mode == 0 and B < 16:
-        return 0.2      # a handful of rows: one flipped mask is a visible fraction of the whole gradient;
-                        # these cases check ragged-shape plumbing, the FP32 mode checks the arithmetic
+        return 0.2      # measured 0.19 (B = 7, reference dims, lambda 10); see the header
     return max(FRO_C[mode] * math.sqrt(32.0 / B), 2e-3 if mode == 0 else 2e-5)
 
 
@@ -74,7 +78,9 @@ def _fro(got, ref):
 
 def max_tol(mode, B):
     # one flipped LeakyReLU mask moves a batch-summed entry by ~1/B of the tensor's max
-    return max(MAX_TOL[mode], (2.5 if mode == 0 else 0.2) / B)
+    if mode == 0:
+        return MAX_TOL[0] / math.sqrt(B) if B >= 16 else 2.5 / B
+    return max(MAX_TOL[1], 0.2 / B)
 
 
 def gp_tol(mode, B):
