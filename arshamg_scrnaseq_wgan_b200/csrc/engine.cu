@@ -445,36 +445,29 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   bool side = !no_side && side_ptr != nullptr && !(epi.aux != nullptr && epi.blend_x != nullptr) &&
               (reinterpret_cast<uintptr_t>(side_ptr) & 15) == 0 && (side_ld & 3) == 0;
   static const bool no_sk = getenv("WGAN_B200_NO_STREAMK") != nullptr;
-  static const bool no_msub2 = getenv("WGAN_B200_PAIR_MSUB2") == nullptr;      // opt-in: measured slower (see below)
   const int sk_pairs = h->sm_cap / 2;
-  // Pair kernel, long reduction over ONE N tile with many rows (the two 6605-deep layer-1 products): 512-row pair
-  // tiles, two 128-row sub-tiles per CTA sharing the B tile in shared memory.  ncu (profiles/r02_ncu_l1_*) showed
-  // these products moving 651 MB through the L2 -> SM path for 340 MB of HBM traffic (5200 B/clk against a ~6300
-  // B/clk chip-wide cap): half of it is the L2-resident B operand, re-streamed once per 256-row tile.  Only taken
-  // together with stream-K (both accumulators fill TMEM, so there is no epilogue overlap to lose).
-  // MEASURED AND REJECTED (opt-in WGAN_B200_PAIR_MSUB2=1, parity-tested): TMA loads fall to 488 MB as predicted but
-  // the layer-1 forward goes 77 -> 92 us and the wgrad 78 -> 104 us: four 48 KB stages cover less memory latency and
-  // the stream-K fix-up tail doubles (ncu: SM-active max 150 K cycles vs 116 K average).  What did help these
-  // products is the producer's burst issue (gemm_sm100.cuh).
+  // (512-row pair tiles -- two 128-row sub-tiles per CTA sharing the B tile, to halve the L2 -> SM re-reads of the
+  // L2-resident operand of the two 6605-deep layer-1 products -- and burst issue in the producer were built, parity-
+  // tested and measured in round 2: TMA loads fell from 651 to 488 MB as predicted but the products got SLOWER
+  // (77 -> 92 us, 78 -> 104 us: four 48 KB stages cover less latency and the stream-K fix-up tail doubles), bursts
+  // changed nothing, and the extra loops in the single-thread issue paths cost 3 % on every GEMM.  Removed again;
+  // DESIGN.md section 4.1 has the numbers, scripts/ubench/l1_stream.cu the load-pattern study.)
   int msub = 1;
   if (!two_cta && h->gemm_msub == 2 && M >= 2 * BM) msub = 2;   // single-CTA kernel, opt-in: measured slower on every WGAN shape
-  if (!no_msub2 && !no_sk && two_cta && nparts == 1 && !raw && n_tiles == 1 && force_splits <= 0 && epi.blend_x == nullptr &&
-      kmax >= 2048 && M >= 8 * BM)
-    msub = 2;
   int nacc, m_tiles, tiles, cluster, m_groups, stages;
   size_t smem;
   int splits[2], kbps[2], total_splits;
   bool streamk;
   for (;;) {
     nacc = (2 * msub * bn <= 512) ? 2 : 1;
-    const int tile_rows = two_cta ? 2 * BM * msub : BM * msub;
+    const int tile_rows = two_cta ? 2 * BM : BM * msub;
     m_tiles = cdiv(M, tile_rows);
     tiles = m_tiles * n_tiles;
     // (1-CTA only) CTAs of a cluster take adjacent M tiles and share the B tile through TMA multicast
     cluster = two_cta ? 1 : h->gemm_cluster;
     while (cluster > 1 && (m_tiles < cluster || (bn / 32) % cluster != 0)) cluster >>= 1;
     m_groups = cdiv(m_tiles, cluster);
-    smem = two_cta ? gemm_smem_bytes(bn / 2, msub, &stages, side) : gemm_smem_bytes(bn, msub, &stages, side);
+    smem = two_cta ? gemm_smem_bytes(bn / 2, 1, &stages, side) : gemm_smem_bytes(bn, msub, &stages, side);
 
     // split-K policy: fill ~2 waves when the output has few tiles, at least 8 k-blocks per split
     total_splits = 0;
@@ -508,20 +501,19 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
       total_splits += sp;
     }
     // Stream-K (CTA-pair kernel): where split-K would be chosen for a single fused product whose tiles are at most
-    // ~4 pairs apiece (8 for the 512-row tiles), every pair instead streams one contiguous range of (tile, K block)
+    // ~4 pairs apiece, every pair instead streams one contiguous range of (tile, K block)
     // units; partial accumulators meet in the workspace and the tile's owner runs the fused epilogue -- no slabs, no
     // finish pass, no idle pairs.  force_splits < 0 forces it (tests), > 0 forces split-K.
     streamk = false;
     if (!no_sk && two_cta && nparts == 1 && !raw && cdiv(parts[0].K, BK) >= 2 &&
-        ((force_splits == 0 && splits[0] > 1 && tiles * (msub == 2 ? 8 : 4) >= sk_pairs) || force_splits < 0) &&
+        ((force_splits == 0 && splits[0] > 1 && tiles * 4 >= sk_pairs) || force_splits < 0) &&
         static_cast<long long>(tiles) * cdiv(parts[0].K, BK) >= sk_pairs &&
-        static_cast<size_t>(sk_pairs) * 2 * msub * SK_SLOT_FLOATS <= h->splitws_n) {
+        static_cast<size_t>(sk_pairs) * 2 * SK_SLOT_FLOATS <= h->splitws_n) {
       streamk = true;
       splits[0] = 1;
       kbps[0] = cdiv(parts[0].K, BK);
       total_splits = 1;
     }
-    if (two_cta && msub == 2 && !streamk) { msub = 1; continue; }     // 512-row tiles only as stream-K
     break;
   }
   if (total_splits > 1 && slab * (ws_slab0 + total_splits) > h->splitws_n) {
@@ -544,8 +536,8 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     const Part& pt = parts[i];
     GemmParams p;
     memset(&p, 0, sizeof p);
-    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, BM * msub, false));
-    else       TRY(make_map_mn3d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, BM * msub / 32));
+    if (!a_mn) TRY(make_map_2d(h, &p.tma_a, pt.A, pt.K, M, pt.lda, 32, two_cta ? BM : BM * msub, false));
+    else       TRY(make_map_mn3d(h, &p.tma_a, pt.A, M, pt.K, pt.lda, two_cta ? BM / 32 : BM * msub / 32));
     if (!b_mn) TRY(make_map_2d(h, &p.tma_b, pt.B, pt.K, N, pt.ldb, 32, two_cta ? bn / 2 : bn / cluster, false));
     else       TRY(make_map_mn3d(h, &p.tma_b, pt.B, N, pt.K, pt.ldb, two_cta ? bn / 64 : bn / 32 / cluster));
     TRY(make_map_out(h, &p.tma_d, out + (direct ? 0 : slab * slab0), N, M, splits[i], ldd, slab));
@@ -573,10 +565,6 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
     p.m_groups = m_groups;
     p.msub = msub;
     p.nacc = nacc;
-    // long reductions stream their operands: burst issue (see the pair kernel's producer); never more than half the ring
-    static const int burst_env = getenv("WGAN_B200_GEMM_BURST") ? atoi(getenv("WGAN_B200_GEMM_BURST")) : 0;
-    p.burst = burst_env > 0 ? burst_env : 1;      // measured equal at 1 and 2 on the real products (r2c), slower at 3
-    if (p.burst > stages / 2) p.burst = stages / 2 > 0 ? stages / 2 : 1;
     // operands that stream from HBM are prefetched into L2 a few K blocks ahead of the smem ring
     static const int l2_prefetch_mb = getenv("WGAN_B200_L2_PREFETCH") ? atoi(getenv("WGAN_B200_L2_PREFETCH")) : 0;
     const size_t pf_min = static_cast<size_t>(l2_prefetch_mb) << 20;      // operands at least this large are prefetched

@@ -92,7 +92,6 @@ struct GemmParams {
   int side_mode;            // 0: side operand (if any) read with per-thread global loads; 1: TMA-staged
   int msub;                 // 128-row sub-tiles per CTA tile (1 or 2): 2 halves the B bytes per FLOP
   int nacc;                 // TMEM accumulator stages: 2 if 2 * msub * bn <= 512 columns, else 1
-  int burst;                // pair kernel producer: K blocks issued back to back once that many ring slots are free (>= 1)
   // stream-K (CTA-pair kernel only): the (tile, K block) units of the whole product are cut into ONE contiguous
   // range per CTA pair, so every pair streams the same number of K blocks whatever the tile count.  A range that
   // starts inside a tile leaves its accumulator in `sk_ws` (+ flag); the pair that holds the tile's first K block
@@ -414,12 +413,9 @@ struct EpiWarp {
   uint32_t nstore, side_issued, side_waited;       // ring positions of the staging boxes / TMA-staged side boxes
 };
 
-// `sub` / `nsub`: 128-row sub-tile of this CTA's tile (the pair kernel's 512-row tiles have two): stream-K slots are
-// [pair][cta][sub]; one flag per (pair, cta, epilogue warp) covers all sub-tiles -- waited for before the first,
-// published / rearmed after the last.
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, int nt, int z, int row0,
                                               uint32_t tcol0, int sk_mode, int sk_cta, int sk_pair, int c_first,
-                                              int c_end, int sub = 0, int nsub = 1) {
+                                              int c_end) {
   constexpr int CPARTS = NUM_EPI_WARPS / 4;
   const EpiParams& e = p.epi;
   const int lane = w.lane, q = w.q, ew = w.ew, cpart = w.cpart;
@@ -435,7 +431,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
   const bool blend_vec = ((reinterpret_cast<uintptr_t>(e.blend_x) & 15) == 0) && ((e.ld_blend & 3) == 0);
   const float beps = (blend && row_ok) ? __ldg(e.blend_eps + row) : 0.0f;
   float sumsq = 0.0f;
-  if (sk_mode == 2 && sub == 0) {                      // the contributors' partials (this warp's share) are written
+  if (sk_mode == 2) {                                  // the contributors' partials (this warp's share) are written
     if (lane == 0) {
       for (int pr = c_first; pr < c_end; ++pr) {
         const unsigned int* f = p.sk_flags + (static_cast<size_t>(pr) * 2 + sk_cta) * NUM_EPI_WARPS + ew;
@@ -463,7 +459,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
       if (sk_mode == 1) {
         // stream-K partial: raw accumulator to this CTA's workspace slot, 512 contiguous bytes per instruction
         tmem_ld32_wait(v);
-        float4* dst = reinterpret_cast<float4*>(p.sk_ws + ((static_cast<size_t>(sk_pair) * 2 + sk_cta) * nsub + sub) * SK_SLOT_FLOATS) +
+        float4* dst = reinterpret_cast<float4*>(p.sk_ws + (static_cast<size_t>(sk_pair) * 2 + sk_cta) * SK_SLOT_FLOATS) +
                       static_cast<size_t>(c) * 8 * 128 + (32 * q + lane);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -486,7 +482,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
           // add the other pairs' partial accumulators of this tile, in pair order (deterministic)
           for (int pr = c_first; pr < c_end; ++pr) {
             const float4* src =
-                reinterpret_cast<const float4*>(p.sk_ws + ((static_cast<size_t>(pr) * 2 + sk_cta) * nsub + sub) * SK_SLOT_FLOATS) +
+                reinterpret_cast<const float4*>(p.sk_ws + (static_cast<size_t>(pr) * 2 + sk_cta) * SK_SLOT_FLOATS) +
                 static_cast<size_t>(c) * 8 * 128 + (32 * q + lane);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -609,7 +605,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
   }
   if (fused && e.row_sumsq != nullptr && row_ok)
     e.row_sumsq[static_cast<size_t>(nt * CPARTS + cpart) * p.M + row] = sumsq;
-  if (sub != nsub - 1) return;
   if (sk_mode == 1) {
     // publish this warp's share of the partial: every lane's stores, then the flag (release)
     __threadfence();
@@ -904,12 +899,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
   // CTA pair (cta_group::2): the pair computes a 256 x bn tile; each CTA holds its 128 rows of A, HALF of
   // the B tile (bn/2 columns) and the accumulator of its own 128 rows.  The leader (cluster rank 0) issues
   // the MMAs for both; all loads of the pair complete on the leader's full barrier.
-  // msub = 2 (long reductions over one N tile, engine.cu): each CTA holds TWO 128-row sub-tiles of A per stage
-  // and both accumulators (2 x bn TMEM columns, single-buffered), so a 512 x bn pair tile streams the B operand
-  // once instead of twice -- these products are bound by the L2 -> SM rate, not by HBM or the tensor pipe.
-  const uint32_t a_bytes = BM * 128u * static_cast<uint32_t>(p.msub);
-  const int TM = 2 * BM * p.msub;              // rows of one pair tile
-  const int CM = BM * p.msub;                  // rows of this CTA's share
+  const uint32_t a_bytes = BM * 128u;
+  const int TM = 2 * BM;                       // rows of one pair tile
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn / 2) * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t epi_base = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;
@@ -981,30 +972,18 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
     while (sched_next(p, sc, pair, npairs, wk)) {
       const int nt = wk.mn % p.n_tiles;
       const int mt = wk.mn / p.n_tiles;
-      const int m0 = mt * TM + static_cast<int>(crank) * CM;      // this CTA's 128 * msub rows
+      const int m0 = mt * TM + static_cast<int>(crank) * BM;      // this CTA's 128 rows
       const int n0 = nt * p.bn + static_cast<int>(crank) * (p.bn / 2);   // this CTA's half of the B tile
       const int kb0 = wk.kb0, kb1 = wk.kb1;
-      // Streaming operands are issued in BURSTS: wait until `burst` ring slots are free, then issue that many K blocks
-      // back to back.  scripts/ubench/l1_stream.cu (the load pattern of the layer-1 products without the MMAs): one
-      // 16 KB box per freed slot streams x at 4.4-4.9 TB/s, two per burst at 5.1-5.8, three or more at 6.1 (consecutive
-      // K blocks of the same rows reach DRAM together); with a 6-slot ring two per burst keeps the prefetch depth.
-      for (int kb = kb0; kb < kb1;) {
-        const int nb = min(p.burst, kb1 - kb);
-        {
-          int s2 = stage;
-          uint32_t ph2 = phase;
-          for (int j = 0; j < nb; ++j) {
-            mbar_wait(empty_bar + 8 * s2, ph2 ^ 1u);
-            if (++s2 == p.stages) { s2 = 0; ph2 ^= 1u; }
-          }
-        }
-        for (int j = 0; j < nb; ++j, ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
         const uint32_t fb = full_leader + 8 * stage;
         const uint32_t sa = smem_base + stage * stage_bytes;
         const uint32_t sb = sa + a_bytes;
         const int k0 = kb * BK;
         if (elect_one()) {
-          // (opt-in experiment, off by default) pull the tile into L2 PREFETCH_DIST K blocks ahead
+          // a streaming operand's HBM latency under load (2-3 us) is more than the 6-stage ring covers at one
+          // stage per 512 MMA cycles: pull its tile into L2 PREFETCH_DIST K blocks ahead, the ring then sees L2 latency
           const int kp = kb + PREFETCH_DIST;
           if (kp < kb1) {
             if (p.prefetch_a) {
@@ -1018,9 +997,9 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
           }
           if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * stage_bytes);   // both CTAs' bytes
           if (!A_MN) {
-            tma_load_2d_2sm(sa, &p.tma_a, fb, k0, m0);                   // box [128 * msub rows][32 k]
+            tma_load_2d_2sm(sa, &p.tma_a, fb, k0, m0);                   // box [128 rows][32 k]
           } else {
-            tma_load_3d_2sm(sa, &p.tma_a, fb, 0, k0, m0 / 32);           // box [4 * msub chunks][32 k][32 m]
+            tma_load_3d_2sm(sa, &p.tma_a, fb, 0, k0, m0 / 32);           // box [4 chunks][32 k][32 m]
           }
           if (!B_MN) {
             tma_load_2d_2sm(sb, &p.tma_b, fb, k0, n0);                   // box [bn/2 rows][32 k]
@@ -1030,7 +1009,6 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-        }
       }
     }
   } else if (warp == 1) {
@@ -1057,25 +1035,21 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
     Work wk;
     for (; sched_next(p, sc, pair, npairs, wk); ++it) {
       const int kb0 = wk.kb0, kb1 = wk.kb1;
-      const int acc = (p.nacc == 2) ? (it & 1) : 0;
-      const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
       tcgen05_after_sync();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.msub * p.bn);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.bn);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar + 8 * stage, phase);
         tcgen05_after_sync();
         const uint32_t a_lo = a_lo0 + stage * stage_step;
         const uint32_t b_lo = b_lo0 + stage * stage_step;
         if (elect_one()) {
-          for (int sub = 0; sub < p.msub; ++sub) {       // both 128-row sub-tiles reuse the B tile in smem
-            const uint32_t a_sub = a_lo + sub * ((BM * 128u) >> 4);
-            const uint32_t d_sub = d_tmem + static_cast<uint32_t>(sub * p.bn);
 #pragma unroll
-            for (int s = 0; s < BK / UMMA_K; ++s)
-              umma_tf32_2cta(d_sub, pack64(a_sub + s * a_kstep, a_hi), pack64(b_lo + s * b_kstep, b_hi), idesc,
-                             (kb > kb0 || s > 0) ? 1u : 0u);
-          }
+          for (int s = 0; s < BK / UMMA_K; ++s)
+            umma_tf32_2cta(d_tmem, pack64(a_lo + s * a_kstep, a_hi), pack64(b_lo + s * b_kstep, b_hi), idesc,
+                           (kb > kb0 || s > 0) ? 1u : 0u);
           // frees the smem slot in BOTH CTAs of the pair when these MMAs retire
           umma_commit_2cta_mc(empty_bar + 8 * stage, cmask);
           if (kb == kb1 - 1) umma_commit_2cta_mc(tfull_bar + 8 * acc, cmask);   // accumulators complete -> both epilogues
@@ -1102,14 +1076,12 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
     for (; sched_next(p, sc, pair, npairs, wk); ++it) {
       const int nt = wk.mn % p.n_tiles;
       const int mt = wk.mn / p.n_tiles;
-      const int acc = (p.nacc == 2) ? (it & 1) : 0;
-      const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tcgen05_after_sync();
-      for (int sub = 0; sub < p.msub; ++sub)
-        epilogue_tile(p, w, nt, wk.z, mt * TM + static_cast<int>(crank) * CM + sub * BM + 32 * w.q,
-                      static_cast<uint32_t>((acc * p.msub + sub) * p.bn), wk.sk_mode, static_cast<int>(crank), pair,
-                      wk.c_first, wk.c_end, sub, p.msub);
+      epilogue_tile(p, w, nt, wk.z, mt * TM + static_cast<int>(crank) * BM + 32 * w.q, static_cast<uint32_t>(acc * p.bn),
+                    wk.sk_mode, static_cast<int>(crank), pair, wk.c_first, wk.c_end);
       // all of this warp's TMEM reads for the tile are done: hand the accumulator back to the leader's MMA warp
       tcgen05_before_sync();
       __syncwarp();

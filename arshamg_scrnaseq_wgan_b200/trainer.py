@@ -501,11 +501,13 @@ class WGANTrainer:
             raise _lib.WganError("draw_minibatch: " + self.lib.wgan_last_error(None).decode())
         return x, z, eps
 
-    def train_iteration_resident(self, it: int, batch: int, seed: int = 0, read: bool = False, counter=None):
+    def train_iteration_resident(self, it: int, batch: int, seed: int = 0, read: bool = False, counter=None,
+                                 generator_update: bool = True):
         """One WGAN-GP iteration with everything drawn on the device: n_critic critic updates
         (fresh minibatch, noise and epsilon each) and one generator update (canonical order),
         or the reference-literal order when cfg.step_order == 'gen_first'.  RNG call ids are
-        it * (n_critic + 1) + k; with `counter` (a device uint32) the base comes from the device."""
+        it * (n_critic + 1) + k; with `counter` (a device uint32) the base comes from the device.
+        generator_update=False runs the n_critic loop alone (BASELINE config 3, the gradient-penalty stress)."""
         cfg = self.cfg
         base = 0 if counter is not None else it * (cfg.n_critic + 1)
         out = {}
@@ -534,10 +536,12 @@ class WGANTrainer:
                 if k + 1 < cfg.n_critic:
                     hold["n"] = draw(k + 1)
                     hold["tok"] = self.critic_prepare(*hold["n"])
-                else:
+                elif generator_update:
                     hold["zg"] = self.noise_prior(batch, seed=seed, call_id=base + cfg.n_critic, counter=counter,
                                                   data_max_value=self._data_max_value)
                     hold["tok"] = self.generator_prepare(hold["zg"])
+                else:
+                    hold["tok"] = 0
 
             r = self.critic_step(x, z, eps, read=read, overlap=ahead if self.world > 1 else None, token=tok)
             if self.world == 1:
@@ -547,12 +551,13 @@ class WGANTrainer:
             tok = hold["tok"]
             if read:
                 out.update(r)
-        r = self.generator_step(zg, read=read, token=tok)
-        if read:
-            out.update(r)
+        if generator_update:
+            r = self.generator_step(zg, read=read, token=tok)
+            if read:
+                out.update(r)
         return out if read else None
 
-    def capture_iteration(self, batch: int, seed: int = 0, start_it: int = 0):
+    def capture_iteration(self, batch: int, seed: int = 0, start_it: int = 0, generator_update: bool = True):
         """Capture one resident-data iteration (every launch of n_critic critic updates + 1 generator
         update, the device RNG, the gather and, in data-parallel runs, the NCCL all-reduces) into a CUDA
         graph and return `replay()`.  The reference pays 4 session calls per iteration [W:184-199]; here a
@@ -566,14 +571,14 @@ class WGANTrainer:
         side = torch.cuda.Stream(device=f"cuda:{self.device}")
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self.train_iteration_resident(0, batch, seed=seed, counter=counter)
+            self.train_iteration_resident(0, batch, seed=seed, counter=counter, generator_update=generator_update)
         torch.cuda.current_stream(self.device).wait_stream(side)
         counter += cfg.n_critic + 1            # the eager warm-up WAS iteration start_it; replays continue from there
         torch.cuda.synchronize()
         l0 = self.launch_count
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.train_iteration_resident(0, batch, seed=seed, counter=counter)
+            self.train_iteration_resident(0, batch, seed=seed, counter=counter, generator_update=generator_update)
             rc = self._pl.wgan_counter_add(C.c_void_p(counter.data_ptr()), cfg.n_critic + 1, self._st())
             if rc != 0:
                 raise _lib.WganError("counter_add: " + self.lib.wgan_last_error(None).decode())
@@ -696,13 +701,14 @@ class WGANTrainer:
             out.update(r)
         return out if read else None
 
-    def train_iteration_host_indices_graph(self, idxs, zs, epss, z_gen, read: bool = True):
+    def train_iteration_host_indices_graph(self, idxs, zs, epss, z_gen, read: bool = True,
+                                           generator_update: bool = True):
         """Same contract as train_iteration_host_indices, replayed as ONE CUDA graph: the host->device
         copies out of the caller's pinned buffers, the gathers, all updates and the device->host copy of the
         loss scalars are graph nodes.  The graph is keyed by the addresses of the pinned host buffers (refill
         the same buffers for every iteration, as a feed ring would); new buffers trigger a re-capture."""
         cfg = self.cfg
-        key = tuple(t.data_ptr() for t in list(idxs) + list(zs) + list(epss) + [z_gen])
+        key = tuple(t.data_ptr() for t in list(idxs) + list(zs) + list(epss) + [z_gen]) + (bool(generator_update),)
         cache = getattr(self, "_hgraph", None)
         if cache is None or cache[0] != key:
             for t in list(idxs) + list(zs) + list(epss) + [z_gen]:
@@ -732,12 +738,32 @@ class WGANTrainer:
                         ready[k].record(copy_stream)
                     d_z[n].copy_(z_gen, non_blocking=True)
                     ready[n].record(copy_stream)
-                for k in range(n):
+
+                def inputs(k):             # gather of update k [W:189-191] + the critic-independent half of the step
                     main.wait_event(ready[k])
                     x = self.gather(d_idx[k])
-                    self.critic_step(x, d_z[k], d_eps[k] if cfg.lambda_gp != 0 else None, read=False)
+                    e = d_eps[k] if cfg.lambda_gp != 0 else None
+                    return x, e, self.critic_prepare(x, d_z[k], e)
+
+                cur, gtok = inputs(0), 0
+                for k in range(n):
+                    x, e, tok = cur
+                    hold = {}
+
+                    def ahead(k=k, hold=hold):     # runs next to the gradient exchange of update k (data-parallel runs)
+                        if k + 1 < n:
+                            hold["n"] = inputs(k + 1)
+                        elif generator_update:
+                            main.wait_event(ready[n])
+                            hold["g"] = self.generator_prepare(d_z[n])
+
+                    self.critic_step(x, d_z[k], e, read=False, overlap=ahead if self.world > 1 else None, token=tok)
+                    if self.world == 1:
+                        ahead()
+                    cur, gtok = hold.get("n"), hold.get("g", 0)
+                if generator_update:
+                    self.generator_step(d_z[n], read=False, token=gtok)
                 main.wait_event(ready[n])
-                self.generator_step(d_z[n], read=False)
                 main.wait_stream(copy_stream)
                 h_scal[0:4].copy_(self._grad_arena[NET_CRITIC][-4:], non_blocking=True)
                 h_scal[4:8].copy_(self._grad_arena[NET_GENERATOR][-4:], non_blocking=True)

@@ -194,7 +194,11 @@ int wgan_draw_minibatch(const float* data_dev, int ld_data, uint32_t n_cells, fl
 /* ---- introspection / test hooks ---- */
 /* D[M,N] = epi(A * B^T-ish): a_mn / b_mn select MN-major operands (see csrc/gemm_sm100.cuh).
  * act: 0 none, 1 LeakyReLU(alpha).  Any of bias/aux/row_scale/row_sumsq may be NULL.
- * force_splits <= 0 lets the engine pick.  *sumsq_tiles receives the number of row_sumsq tiles. */
+ * force_splits == 0 lets the engine pick (split-K or stream-K), > 0 forces that many split-K slabs, < 0 forces
+ * stream-K.  *sumsq_tiles receives the number of row_sumsq tiles.
+ * Unlike the step entry points (which stage or own their operands) this hook hands A / B to TMA as they are: an
+ * MN-major operand is read in whole 32-float chunks, so its LAST row must be followed by 124 readable bytes
+ * (one spare row is enough). */
 int wgan_gemm(wgan_handle* h, int a_mn, int b_mn, const float* A, int lda, const float* B, int ldb,
               float* D, int ldd, int M, int N, int K, const float* bias, int act, const float* aux,
               int ld_aux, const float* row_scale, float* row_sumsq, int* sumsq_tiles,

@@ -37,3 +37,23 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
                          timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert not [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+
+
+def test_every_baseline_config_has_a_reference_arm_with_the_same_workload_text():
+    """--config 3 / 4 / 5: the reference arm prints the contract line with the metric, unit and config.workload the
+    B200 arm of that configuration prints (both arms take them from bench.CONFIGS)."""
+    import pytest
+    sys.path.insert(0, ROOT)
+    import bench
+    for cid in (3, 4, 5):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", str(cid),
+                              "--batch", "64", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                             timeout=600, cwd=ROOT)
+        assert out.returncode == 0, out.stderr[-2000:]
+        d = json.loads([l for l in out.stdout.splitlines() if l.strip().startswith("{")][0])
+        c = bench.CONFIGS[cid]
+        assert d["metric"] == c["metric"] and d["unit"] == c["unit"] and d["scaling"] == c["scaling"]
+        assert d["config"]["workload"] == c["workload"] and d["config"]["baseline_config"] == cid
+        assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"]
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"workload": c["workload"]') >= 3      # reference arm, training arm, sampling arm
