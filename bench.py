@@ -387,7 +387,9 @@ def dominant_kernel_roofline(tr, batch, torch, pk, tf32_peak, n_critic=5, genera
     # `ncu --set full` captures (reference dims, batch 4096 only); null for shapes that were not captured
     NCU_TRAFFIC = {"critic layer-1 forward": (342.23e6 + 11.76e6, "profiles/r02_ncu_full_critic_l1_forward.txt"),
                    "critic layer-1 weight gradient": (355.40e6 + 8.31e6, "profiles/r02_ncu_full_critic_l1_wgrad.txt"),
-                   "generator output forward [": (26.50e6 + 56.78e6, "profiles/r01_ncu_full_generator_output.txt")}
+                   "generator output forward [": (26.54e6 + 55.65e6, "profiles/r02_ncu_full_generator_output.txt"),
+                   "generator output forward with the fused interpolate": (168.31e6 + 165.39e6,
+                                                                           "profiles/r02_ncu_full_generator_output.txt")}
     traffic, traffic_src = None, None
     if G == 6605 and batch == 4096:
         for key, (t, src) in NCU_TRAFFIC.items():

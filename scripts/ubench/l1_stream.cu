@@ -110,8 +110,20 @@ int main() {
   cudaFuncSetAttribute(l1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   struct V { const char* name; int coupled, use_b, a_st, b_st, consume, burst; int promo; int f32; };
   V vs[] = {
-    {"coupled A+B, 6 x 32 KB burst 1 (GEMM today), consumer 512", 1, 1, 6, 0, 512, 1, 2, 0},
-    {"coupled A+B, 6 x 32 KB burst 2, consumer 512", 1, 1, 6, 0, 512, 2, 2, 0},
+    {"A tiles [128][128 B], 6 x 16 KB, one box per freed slot", 1, 0, 6, 0, 0, 1, 2, 0},
+    {"A tiles, 12 x 16 KB, burst 1", 1, 0, 12, 0, 0, 1, 2, 0},
+    {"A tiles, 12 x 16 KB, burst 2", 1, 0, 12, 0, 0, 2, 2, 0},
+    {"A tiles, 12 x 16 KB, burst 3", 1, 0, 12, 0, 0, 3, 2, 0},
+    {"A tiles, 12 x 16 KB, burst 4", 1, 0, 12, 0, 0, 4, 2, 0},
+    {"A tiles, 12 x 16 KB, burst 4, L2 promotion none", 1, 0, 12, 0, 0, 4, 0, 0},
+    {"A linear 16 KB pieces (cp.async.bulk), CTA-contiguous", 1, 0, 12, 0, 0, 1, 2, 2},
+    {"coupled A+B, 6 x 32 KB burst 1 (the GEMM's ring)", 1, 1, 6, 0, 0, 1, 2, 0},
+    {"coupled A+B, 6 x 32 KB burst 2", 1, 1, 6, 0, 0, 2, 2, 0},
+    {"coupled A+B, 6 x 32 KB burst 1, consumer 512 clk", 1, 1, 6, 0, 512, 1, 2, 0},
+    {"coupled A+B, 6 x 32 KB burst 2, consumer 512 clk", 1, 1, 6, 0, 512, 2, 2, 0},
+    {"coupled A+B, 6 x 32 KB burst 3, consumer 512 clk", 1, 1, 6, 0, 512, 3, 2, 0},
+    {"decoupled A 10 x 16 KB burst 4, B 3 x 16 KB", 0, 1, 10, 3, 0, 4, 2, 0},
+    {"decoupled A 10 burst 4 / B 3, consumer 512 clk", 0, 1, 10, 3, 512, 4, 2, 0},
   };
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (auto& v : vs) {
