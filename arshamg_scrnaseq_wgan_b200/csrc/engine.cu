@@ -445,8 +445,10 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   bool side = !no_side && side_ptr != nullptr && !(epi.aux != nullptr && epi.blend_x != nullptr) &&
               (reinterpret_cast<uintptr_t>(side_ptr) & 15) == 0 && (side_ld & 3) == 0;
   static const bool no_sk = getenv("WGAN_B200_NO_STREAMK") != nullptr;
-  // pairs per tile up to which stream-K replaces split-K + finish (6: the 4096-row layer-1 products, 16 tiles on 74 pairs)
-  static const int sk_max_contrib = getenv("WGAN_B200_SK_MAX_CONTRIB") ? atoi(getenv("WGAN_B200_SK_MAX_CONTRIB")) : 6;
+  // pairs per tile up to which stream-K replaces split-K + finish.  4 = the 12288-row layer-1 products (48 / 26 tiles on
+  // 74 pairs); 6 would also take the 4096-row ones (16 tiles) and was measured SLOWER on the whole iteration
+  // (379.9 vs 389.0 iters/s, explicit form: the owner's serial fix-up over 4-5 partials costs more than the finish pass)
+  static const int sk_max_contrib = getenv("WGAN_B200_SK_MAX_CONTRIB") ? atoi(getenv("WGAN_B200_SK_MAX_CONTRIB")) : 4;
   const int sk_pairs = h->sm_cap / 2;
   // (512-row pair tiles -- two 128-row sub-tiles per CTA sharing the B tile, to halve the L2 -> SM re-reads of the
   // L2-resident operand of the two 6605-deep layer-1 products -- and burst issue in the producer were built, parity-
@@ -503,7 +505,7 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
       total_splits += sp;
     }
     // Stream-K (CTA-pair kernel): where split-K would be chosen for a single fused product whose tiles are at most
-    // ~6 pairs apiece, every pair instead streams one contiguous range of (tile, K block)
+    // ~4 pairs apiece, every pair instead streams one contiguous range of (tile, K block)
     // units; partial accumulators meet in the workspace and the tile's owner runs the fused epilogue -- no slabs, no
     // finish pass, no idle pairs.  force_splits < 0 forces it (tests), > 0 forces split-K.
     streamk = false;
