@@ -104,6 +104,8 @@ struct wgan_handle {
   int dp_rank, dp_world, dp_blocks; bool dp_connected;
   bool dp_early_trigger;                   // every rank has its own GPU (wgan_dp_connect): see dp_allreduce_kernel
   cudaStream_t dp_stream; cudaEvent_t dp_fork, dp_join;   // wgan_generator_grads_exchange: exchange next to the backward pass
+  // bias-gradient / loss column sums run on a second stream next to the weight-gradient GEMMs (they only read)
+  cudaStream_t aux_stream; cudaEvent_t aux_fork, aux_join; bool aux_overlap;
   float* dp_peer[WGAN_DP_MAX_WORLD];       // window base of every rank as mapped here (own rank: dp_win)
   bool dp_peer_ipc[WGAN_DP_MAX_WORLD];     // opened with cudaIpcOpenMemHandle (closed in wgan_destroy)
 
@@ -800,6 +802,9 @@ void wgan_destroy(wgan_handle* h) {
     cudaFree(h->powers[n]);
   }
   if (h->dp_stream) cudaStreamDestroy(h->dp_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->aux_fork) cudaEventDestroy(h->aux_fork);
+  if (h->aux_join) cudaEventDestroy(h->aux_join);
   if (h->dp_fork) cudaEventDestroy(h->dp_fork);
   if (h->dp_join) cudaEventDestroy(h->dp_join);
   cudaFree(h->dp_win);
@@ -833,6 +838,8 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->dp_blocks = 32;
   h->dp_early_trigger = false;
   h->dp_stream = nullptr; h->dp_fork = nullptr; h->dp_join = nullptr;
+  h->aux_stream = nullptr; h->aux_fork = nullptr; h->aux_join = nullptr;
+  h->aux_overlap = getenv("WGAN_B200_NO_AUX_OVERLAP") == nullptr;
   if (const char* env = getenv("WGAN_B200_DP_BLOCKS")) {
     const int b = atoi(env);
     if (b >= 1 && b <= DP_MAX_BLOCKS) h->dp_blocks = b;
@@ -926,6 +933,10 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->dp_flags_off = h->dp_stage_off + static_cast<size_t>(h->dp_world > 1 ? h->dp_world : 0) * h->dp_stage_stride;
   h->dp_win_bytes = (h->dp_flags_off + DP_FLAG_WORDS) * 4;
   if (cudaMalloc(&h->dp_win, h->dp_win_bytes) != cudaSuccess) return fail("cudaMalloc(gradient window) failed");
+  if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming) != cudaSuccess)
+    return fail("creating the auxiliary stream failed");
   if (h->dp_world > 1) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -1243,9 +1254,16 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
     TRY(gemm1(h, false, true, h1_hat, Hdl, W2, ldw2, h->v2, Hdl, Bl, Hd, Hd, epi_mask(h2_hat, Hdl, a), s));
   }
 
-  // weight gradients
-  TRY(gemm1(h, true, true, h->xcat, Gl, h->d1, Hdl, h->Gr(T_W1), ldw1, G, Hd, T, epi_none(), s));
-  TRY(gemm1(h, true, true, h->h1, Hdl, h->d2, Hdl, h->Gr(T_W2), ldw2, Hd, Hd, T, epi_none(), s));
+  // Bias gradients, the layer-3 weight gradient and the loss scalars are column sums over buffers that are final by
+  // now; they run on the auxiliary stream NEXT TO the two weight-gradient GEMMs below (small non-persistent grids
+  // that co-reside with the persistent GEMM CTAs), joined before the function returns.
+  const bool ov = h->aux_overlap;
+  cudaStream_t sc_stream = s;
+  if (ov) {
+    CK(cudaEventRecord(h->aux_fork, s));
+    CK(cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+    sc_stream = h->aux_stream;
+  }
   {
     ColsumJob jobs[3];
     memset(jobs, 0, sizeof jobs);
@@ -1264,8 +1282,13 @@ int wgan_critic_grads(wgan_handle* h, const float* x_dev, int ldx, const float* 
     float* sc = h->scalars(WGAN_NET_CRITIC);
     const SumJob sums[3] = {{h->dout, sc + WGAN_S_DFAKE, Bl, invB}, {h->dout + real0, sc + WGAN_S_DREAL, Bl, invB},
                             {h->pen, sc + WGAN_S_GP, gp ? Bl : 0, h->cfg.lambda_gp * invB}};
-    TRY(colsum_jobs(h, jobs, 3, s, h->Gr(T_B3), sums, 3));
+    TRY(colsum_jobs(h, jobs, 3, sc_stream, h->Gr(T_B3), sums, 3));
   }
+  if (ov) CK(cudaEventRecord(h->aux_join, h->aux_stream));
+  // weight gradients
+  TRY(gemm1(h, true, true, h->xcat, Gl, h->d1, Hdl, h->Gr(T_W1), ldw1, G, Hd, T, epi_none(), s));
+  TRY(gemm1(h, true, true, h->h1, Hdl, h->d2, Hdl, h->Gr(T_W2), ldw2, Hd, Hd, T, epi_none(), s));
+  if (ov) CK(cudaStreamWaitEvent(s, h->aux_join, 0));
   return 0;
 }
 
@@ -1333,9 +1356,16 @@ static int generator_grads_impl(wgan_handle* h, const float* z_dev, int ldz, int
   // generator backward
   const float* Wg3 = h->P(T_WG3); const int ldg3 = h->td[T_WG3].ld;
   const float* Wg2 = h->P(T_WG2); const int ldg2 = h->td[T_WG2].ld;
-  TRY(gemm1(h, true, true, h->gh2, Hgl, d3, Gl, h->Gr(T_WG3), ldg3, Hg, G, Bl, epi_none(), s));
+  const bool ov = h->aux_overlap;
   {
-    // output-bias gradient now, while d3 (108 MB at batch 4096) is still partly L2-resident
+    // output-bias gradient (column sum of d3, 108 MB at batch 4096) on the auxiliary stream NEXT TO the output
+    // layer's weight gradient, which reads the same d3
+    cudaStream_t sc_stream = s;
+    if (ov) {
+      CK(cudaEventRecord(h->aux_fork, s));
+      CK(cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+      sc_stream = h->aux_stream;
+    }
     ColsumJob jb;
     memset(&jb, 0, sizeof jb);
     jb.seg[0] = ColsumSeg{d3, Bl, Gl, 1.0f};
@@ -1343,8 +1373,11 @@ static int generator_grads_impl(wgan_handle* h, const float* z_dev, int ldz, int
     // (the loss scalar rides along: with the exchange below it must be final before the output layer's range goes out)
     float* sc = h->scalars(WGAN_NET_GENERATOR);
     const SumJob gj = {h->dout, sc + WGAN_S_DFAKE, Bl, invB};          // mean D(G(z)) for obj_g [W:138]
-    TRY(colsum_jobs(h, &jb, 1, s, nullptr, &gj, 1));
+    TRY(colsum_jobs(h, &jb, 1, sc_stream, nullptr, &gj, 1));
+    if (ov) CK(cudaEventRecord(h->aux_join, h->aux_stream));
   }
+  TRY(gemm1(h, true, true, h->gh2, Hgl, d3, Gl, h->Gr(T_WG3), ldg3, Hg, G, Bl, epi_none(), s));
+  if (ov) CK(cudaStreamWaitEvent(s, h->aux_join, 0));
   // Data-parallel exchange, first part: the output layer's gradients (kernel + bias, 90 % of the arena) and the
   // scalar tail are final -- sum them over the ranks on a second stream WHILE the rest of the backward pass runs
   // (measured on 2 GPUs: the 17.6 MB exchange after the step costs 62 us fully exposed; ~125 us of backward work
