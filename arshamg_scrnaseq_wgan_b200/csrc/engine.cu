@@ -263,12 +263,16 @@ int pick_bn(int N) {
 // N tile of the CTA-pair kernel: cta_group::2 runs at N/2 cycles per UMMA_K step with no fixed cost, so
 // only padding and A re-reads matter; each CTA loads bn/2 columns, which must be whole 32-column boxes
 // for an MN-major B (bn % 64 == 0).
-int pick_bn_2cta(int N, bool b_mn) {
+int pick_bn_2cta(int N, bool b_mn, bool long_k = false) {
   const int step = b_mn ? 64 : 32;
   int best = 256;
   long best_cost = 1L << 60;
   for (int bn = 256; bn >= step; bn -= step) {
-    const long cost = static_cast<long>(cdiv(N, bn)) * (bn + 48);
+    // long reductions stream their operands: per K block a CTA ingests 16 KB of A + bn/2 * 128 B of B at ~51 B/clk
+    // (scripts/ubench/tma_rate.cu) against 2 * bn MMA cycles, so narrow tiles that re-stream A more often lose
+    // (N = 800: 4 x 256 instead of 5 x 192, BASELINE config 4)
+    const long per_kb = long_k ? std::max<long>(2 * bn, (16384 + 64 * bn) * 10 / 512) : bn + 48;
+    const long cost = static_cast<long>(cdiv(N, bn)) * per_kb;
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -425,13 +429,16 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   const double waste1 = static_cast<double>(cdiv(M, BM)) * BM / M;
   const bool two_cta = h->gemm_2cta != 0 && waste2 <= 1.10 * waste1;
   static const int bn_cap = getenv("WGAN_B200_GEMM_BN") ? atoi(getenv("WGAN_B200_GEMM_BN")) : 0;          // experiments
-  int bn = two_cta ? pick_bn_2cta(N, b_mn) : pick_bn(N);
+  int kmax = 0;
+  for (int i = 0; i < nparts; ++i) kmax = parts[i].K > kmax ? parts[i].K : kmax;
+  static const bool longk_bn = getenv("WGAN_B200_NO_LONGK_BN") == nullptr;      // A/B switch
+  // (row-major activations as A only: the weight gradient of the same wide layer measured 651 us with 5 x 192
+  // tiles and 741 us with 4 x 256, the forward product 999 us and 739 us)
+  int bn = two_cta ? pick_bn_2cta(N, b_mn, longk_bn && kmax >= 4096 && !a_mn) : pick_bn(N);
   if (!two_cta && bn_cap >= 32 && bn_cap % 32 == 0 && bn > bn_cap) bn = bn_cap;
   // latency-bound outputs (the pair tiles would cover less than half of the SMs): halve the tile width, which
   // halves both the MMA time per K block and the epilogue of the single tile each CTA pair owns
   static const bool narrow_small = getenv("WGAN_B200_NO_NARROW_SMALL") == nullptr;
-  int kmax = 0;
-  for (int i = 0; i < nparts; ++i) kmax = parts[i].K > kmax ? parts[i].K : kmax;
   // (not for long reductions over many rows: a second N tile would stream the A operand twice)
   if (narrow_small && two_cta && N > 128 && N <= bn && (kmax < 1024 || M <= 2 * BM) &&
       cdiv(M, 2 * BM) * cdiv(N, bn) * nparts * 2 <= h->num_sms / 2) {
