@@ -436,6 +436,16 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
   // tiles and 741 us with 4 x 256, the forward product 999 us and 739 us)
   int bn = two_cta ? pick_bn_2cta(N, b_mn, longk_bn && kmax >= 4096 && !a_mn) : pick_bn(N);
   if (!two_cta && bn_cap >= 32 && bn_cap % 32 == 0 && bn > bn_cap) bn = bn_cap;
+  // a nearly empty second wave (e.g. [4096 x 600] x [600 x 600]: 5 x 16 = 80 tiles of 128 columns on 74 pairs): widen
+  // the tile to the smallest width whose tiles fit one wave (192 -> 64 tiles)
+  static const bool one_wave = getenv("WGAN_B200_NO_ONE_WAVE") == nullptr;
+  if (one_wave && two_cta && nparts == 1) {
+    const int pairs = h->sm_cap / 2, mt2 = cdiv(M, 2 * BM), step = b_mn ? 64 : 32;
+    const int t0 = mt2 * cdiv(N, bn);
+    if (t0 > pairs && 2 * t0 < 3 * pairs)
+      for (int w = bn + step; w <= 256; w += step)
+        if (mt2 * cdiv(N, w) <= pairs) { bn = w; break; }
+  }
   // latency-bound outputs (the pair tiles would cover less than half of the SMs): halve the tile width, which
   // halves both the MMA time per K block and the epilogue of the single tile each CTA pair owns
   static const bool narrow_small = getenv("WGAN_B200_NO_NARROW_SMALL") == nullptr;
