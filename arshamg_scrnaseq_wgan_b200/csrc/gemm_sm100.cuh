@@ -976,6 +976,17 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
       const int n0 = nt * p.bn + static_cast<int>(crank) * (p.bn / 2);   // this CTA's half of the B tile
       const int kb0 = wk.kb0, kb1 = wk.kb1;
       for (int kb = kb0; kb < kb1; ++kb) {
+#if defined(WGAN_PAIR_BURST) && WGAN_PAIR_BURST > 1
+        // diagnostic / experimental build: issue K blocks in groups -- wait until the whole group's slots are free
+        if ((kb - kb0) % WGAN_PAIR_BURST == 0) {
+          int s2 = stage;
+          uint32_t ph2 = phase;
+          for (int j = 0; j < WGAN_PAIR_BURST && kb + j < kb1; ++j) {
+            mbar_wait(empty_bar + 8 * s2, ph2 ^ 1u);
+            if (++s2 == p.stages) { s2 = 0; ph2 ^= 1u; }
+          }
+        }
+#endif
         mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
         const uint32_t fb = full_leader + 8 * stage;
         const uint32_t sa = smem_base + stage * stage_bytes;
@@ -995,17 +1006,23 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
               else       tma_prefetch_3d(&p.tma_b, 0, kp * BK, n0 / 32);
             }
           }
+#ifdef WGAN_DIAG_NO_B       // diagnostic build (scripts/diag_build.sh): stream A only -- results are garbage
+          if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * a_bytes);
+#else
           if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * stage_bytes);   // both CTAs' bytes
+#endif
           if (!A_MN) {
             tma_load_2d_2sm(sa, &p.tma_a, fb, k0, m0);                   // box [128 rows][32 k]
           } else {
             tma_load_3d_2sm(sa, &p.tma_a, fb, 0, k0, m0 / 32);           // box [4 chunks][32 k][32 m]
           }
+#ifndef WGAN_DIAG_NO_B
           if (!B_MN) {
             tma_load_2d_2sm(sb, &p.tma_b, fb, k0, n0);                   // box [bn/2 rows][32 k]
           } else {
             tma_load_3d_2sm(sb, &p.tma_b, fb, 0, k0, n0 / 32);           // box [bn/64 chunks][32 k][32 n]
           }
+#endif
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -1046,10 +1063,14 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
         const uint32_t a_lo = a_lo0 + stage * stage_step;
         const uint32_t b_lo = b_lo0 + stage * stage_step;
         if (elect_one()) {
+#ifdef WGAN_DIAG_NO_MMA      // diagnostic build: one MMA per K block instead of four (keeps the commit semantics)
+          umma_tf32_2cta(d_tmem, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc, (kb > kb0) ? 1u : 0u);
+#else
 #pragma unroll
           for (int s = 0; s < BK / UMMA_K; ++s)
             umma_tf32_2cta(d_tmem, pack64(a_lo + s * a_kstep, a_hi), pack64(b_lo + s * b_kstep, b_hi), idesc,
                            (kb > kb0 || s > 0) ? 1u : 0u);
+#endif
           // frees the smem slot in BOTH CTAs of the pair when these MMAs retire
           umma_commit_2cta_mc(empty_bar + 8 * stage, cmask);
           if (kb == kb1 - 1) umma_commit_2cta_mc(tfull_bar + 8 * acc, cmask);   // accumulators complete -> both epilogues

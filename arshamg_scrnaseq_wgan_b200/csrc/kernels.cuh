@@ -254,8 +254,13 @@ __global__ void gp_coef_kernel(const float* __restrict__ nsq, int ntiles, int ti
   pdl_wait();
   const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    // the tiles' partial sums of squares (52 at the reference dims) are read by different lanes and combined by an
+    // xor butterfly (commutative at every stage: all lanes hold the same bits) instead of one serial chain of
+    // L2-latency loads per row
     float s = 0.0f;
-    for (int t = 0; t < ntiles; ++t) s += nsq[static_cast<size_t>(t) * tile_stride + r];
+    for (int t = lane; t < ntiles; t += 32) s += nsq[static_cast<size_t>(t) * tile_stride + r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float n = sqrtf(s);
     const float cb = two_lambda_over_B * (n - 1.0f) / n;
     if (lane == 0) {

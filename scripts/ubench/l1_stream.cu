@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(96, 1) l1_stream_kernel(const __grid_constant_
   }
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const bool same_buffer = argc > 1;      // any argument: re-read the SAME buffer every launch (like scripts/profile_gemm.py)
   void* fn = nullptr; cudaDriverEntryPointQueryResult q;
   cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
   EncodeTiledFn encode = (EncodeTiledFn)fn;
@@ -136,7 +137,7 @@ int main() {
       encode(&p2.a, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, A2, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE); }
     float best = 1e9;
     for (int rep = 0; rep < 4; ++rep) {
-      l1_stream_kernel<<<148, 96, 225 * 1024>>>(p2);      // reads the other A buffer: evicts this one with CLEAN lines
+      if (!same_buffer) l1_stream_kernel<<<148, 96, 225 * 1024>>>(p2);      // reads the other A buffer: evicts this one with CLEAN lines
       cudaEventRecord(e0);
       l1_stream_kernel<<<148, 96, 225 * 1024>>>(p);
       cudaEventRecord(e1);
@@ -180,7 +181,7 @@ int main() {
                                q->total_kb = M / 32; q->row_tiles = (K + 127) / 128; q->out = d; }
       float best = 1e9;
       for (int rep = 0; rep < 4; ++rep) {
-        l1_stream_kernel<<<148, 96, 225 * 1024>>>(w2);
+        if (!same_buffer) l1_stream_kernel<<<148, 96, 225 * 1024>>>(w2);
         cudaEventRecord(e0);
         l1_stream_kernel<<<148, 96, 225 * 1024>>>(w);
         cudaEventRecord(e1);
