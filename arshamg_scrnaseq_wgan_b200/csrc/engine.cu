@@ -602,6 +602,35 @@ int run_gemm(wgan_handle* h, bool a_mn, bool b_mn, const Part* parts, int nparts
       p.sk_units = static_cast<long long>(tiles) * p.total_kb;
       p.sk_ws = h->splitws;
       p.sk_flags = h->sk_flags;
+      {
+        // Unit ranges.  Phase stamps of the layer-1 products (scripts/diag_stamps.py): every pair finishes its MMAs
+        // within ~4 us of the others, a partial's dump + flag takes ~4 us, and a tile's owner then needs 6-10 us for
+        // the fix-up; a pair whose LAST segment is a partial therefore gets `shift` units less (its dump overlaps the
+        // others' last K blocks) and the rest is spread over all pairs.
+        static const int shift_env = getenv("WGAN_B200_SK_SHIFT") ? atoi(getenv("WGAN_B200_SK_SHIFT")) : 9;
+        const int P = sk_pairs, KB = p.total_kb;
+        const long long U = p.sk_units;
+        const int shift = static_cast<int>(std::min<long long>(shift_env, U / P / 8));
+        long long b[80];
+        for (int q = 0; q <= P; ++q) b[q] = static_cast<long long>(q) * U / P;
+        for (int iter = 0; iter < 3 && shift > 0; ++iter) {
+          bool late[80];
+          int nlate = 0;
+          for (int q = 0; q < P; ++q) {
+            const long long te = (b[q + 1] - 1) / KB;                 // tile of the pair's last unit
+            late[q] = b[q + 1] > b[q] && std::max(b[q], te * KB) > te * KB;   // its last segment starts inside that tile
+            nlate += late[q] ? 1 : 0;
+          }
+          const double base = (static_cast<double>(U) + static_cast<double>(shift) * nlate) / P;
+          double acc = 0.0;
+          for (int q = 0; q < P; ++q) {
+            acc += base - (late[q] ? shift : 0);
+            b[q + 1] = std::min<long long>(U, std::max<long long>(b[q] + 1, static_cast<long long>(acc + 0.5)));
+          }
+          b[P] = U;
+        }
+        for (int q = 0; q <= P; ++q) p.sk_b[q] = static_cast<int>(b[q]);
+      }
     }
     const int grid = streamk ? sk_pairs : m_groups * n_tiles * splits[i];   // cluster tiles; launch_tc caps at residency
     if (two_cta) {
@@ -1789,3 +1818,10 @@ int wgan_get_buffer(wgan_handle* h, const char* name, float** dev_ptr, int* rows
 }
 
 }  // extern "C"
+
+#ifdef WGAN_DIAG_STAMPS
+// diagnostic build only (scripts/diag_build.sh): phase stamps [block][8] of the pair kernel's last launch
+extern "C" int wgan_diag_read_stamps(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, wg::g_diag_stamps, sizeof(unsigned long long) * 160 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -38,6 +38,20 @@
 
 namespace wg {
 
+#ifdef WGAN_DIAG_STAMPS      // diagnostic build: per-CTA phase time stamps of the pair kernel's last launch
+__device__ unsigned long long g_diag_stamps[160][8];
+__device__ __forceinline__ unsigned long long diag_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DIAG_STAMP(i) do { if (w.ew == 0 && lane == 0) g_diag_stamps[blockIdx.x][i] = diag_now(); } while (0)
+#define g_diag_mode_store(mode, it) do { if (w.ew == 0 && lane == 0) g_diag_stamps[blockIdx.x][7] = (it == 0 ? 0ull : g_diag_stamps[blockIdx.x][7]) | (static_cast<unsigned long long>(mode + 1) << (8 * it)); } while (0)
+#else
+#define DIAG_STAMP(i) do { } while (0)
+#define g_diag_mode_store(mode, it) do { } while (0)
+#endif
+
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 32;           // 32 tf32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;        // 32 B / sizeof(tf32)
@@ -99,6 +113,9 @@ struct GemmParams {
   int streamk;              // 0 = tiles (x splits) round-robin, 1 = stream-K
   long long sk_units;       // m_tiles * n_tiles * total_kb
   float* sk_ws;             // partial accumulators [pair][cta 2][chunk 8][j 8][row 128] float4
+  // unit range of pair q = [sk_b[q], sk_b[q + 1]): equal shares, except that a pair whose LAST segment is a partial
+  // gets a few units less -- its dump (~4 us) then ends when the tile's owner is ready for it (engine.cu)
+  int sk_b[80];
   unsigned int* sk_flags;   // [pair][cta 2][epilogue warp]: 1 = that warp's share of the partial is written
   EpiParams epi;
 };
@@ -358,8 +375,8 @@ struct Sched {
   int tile, step;         // round-robin over tiles x splits
   long long u, u_end;     // stream-K unit range of this pair
 };
-__device__ __forceinline__ long long sk_first_unit(const GemmParams& p, int pair, int npairs) {
-  return static_cast<long long>(pair) * p.sk_units / npairs;
+__device__ __forceinline__ long long sk_first_unit(const GemmParams& p, int pair, int /*npairs*/) {
+  return p.sk_b[pair];
 }
 __device__ __forceinline__ void sched_init(const GemmParams& p, Sched& s, int pair, int npairs) {
   s.tile = pair; s.step = npairs;
@@ -479,19 +496,40 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
           tmem_ld32_wait(v);
         }
         if (sk_mode == 2) {
-          // add the other pairs' partial accumulators of this tile, in pair order (deterministic)
-          for (int pr = c_first; pr < c_end; ++pr) {
-            const float4* src =
-                reinterpret_cast<const float4*>(p.sk_ws + (static_cast<size_t>(pr) * 2 + sk_cta) * SK_SLOT_FLOATS) +
-                static_cast<size_t>(c) * 8 * 128 + (32 * q + lane);
+          // add the other pairs' partial accumulators of this tile, in pair order (deterministic).  Two contributors'
+          // loads are in flight together: this fix-up sits on the kernel's critical path (diagnostic builds: the
+          // stream-K tail is 16 of the layer-1 products' 76 us) and each load is an L2 round trip.
+          const size_t slot_off = static_cast<size_t>(c) * 8 * 128 + (32 * q + lane);
+          auto slot = [&](int pr) {
+            return reinterpret_cast<const float4*>(p.sk_ws + (static_cast<size_t>(pr) * 2 + sk_cta) * SK_SLOT_FLOATS) + slot_off;
+          };
+          auto add8 = [&](const float4 (&u)[8]) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 u = __ldcg(src + j * 128);          // written by another SM during this launch: L2 only
-              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + u.x);
-              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + u.y);
-              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + u.z);
-              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + u.w);
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + u[j].x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + u[j].y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + u[j].z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + u[j].w);
             }
+          };
+          int pr = c_first;
+          for (; pr + 1 < c_end; pr += 2) {
+            float4 u0[8], u1[8];
+            const float4* s0 = slot(pr);
+            const float4* s1 = slot(pr + 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u0[j] = __ldcg(s0 + j * 128);   // written by another SM during this launch: L2 only
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u1[j] = __ldcg(s1 + j * 128);
+            add8(u0);
+            add8(u1);
+          }
+          if (pr < c_end) {
+            float4 u0[8];
+            const float4* s0 = slot(pr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u0[j] = __ldcg(s0 + j * 128);
+            add8(u0);
           }
         }
         if (e.act == 1) {
@@ -960,6 +998,9 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
   // the grid that is resident can finish on its own -- no co-residency requirement, whatever else holds SMs.
   const int npairs = gridDim.x / 2;
   const int pair = p.streamk ? npairs - 1 - static_cast<int>(blockIdx.x / 2) : static_cast<int>(blockIdx.x / 2);
+#ifdef WGAN_DIAG_STAMPS
+  if (threadIdx.x == 64) g_diag_stamps[blockIdx.x][0] = diag_now();
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -1063,6 +1104,13 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
         const uint32_t a_lo = a_lo0 + stage * stage_step;
         const uint32_t b_lo = b_lo0 + stage * stage_step;
         if (elect_one()) {
+#if defined(WGAN_DIAG_SW_CONSUMER)   // diagnostic build: no tensor-core work at all, the slot is freed by plain arrives
+          mbar_arrive(empty_bar + 8 * stage);
+          mbar_arrive_cluster(empty_bar + 8 * stage, 1);
+          if (kb == kb1 - 1) { mbar_arrive(tfull_bar + 8 * acc); mbar_arrive_cluster(tfull_bar + 8 * acc, 1); }
+        }
+        if (false) {
+#endif
 #ifdef WGAN_DIAG_NO_MMA      // diagnostic build: one MMA per K block instead of four (keeps the commit semantics)
           umma_tf32_2cta(d_tmem, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc, (kb > kb0) ? 1u : 0u);
 #else
@@ -1099,16 +1147,23 @@ gemm_tf32_2cta_kernel(const __grid_constant__ GemmParams p) {
       const int mt = wk.mn / p.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if (it == 0) DIAG_STAMP(1);                 // first segment: waiting for its accumulator starts
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tcgen05_after_sync();
+      DIAG_STAMP(2 + 2 * (it > 0 ? 1 : 0));       // accumulator of segment `it` complete (2: first, 4: last)
+      g_diag_mode_store(wk.sk_mode, it);
+#ifndef WGAN_DIAG_NO_EPI     // diagnostic build: accumulators are dropped (no partials, no fix-up, no stores)
       epilogue_tile(p, w, nt, wk.z, mt * TM + static_cast<int>(crank) * BM + 32 * w.q, static_cast<uint32_t>(acc * p.bn),
                     wk.sk_mode, static_cast<int>(crank), pair, wk.c_first, wk.c_end);
+#endif
+      DIAG_STAMP(3 + 2 * (it > 0 ? 1 : 0));       // epilogue of segment `it` done (3: first, 5: last)
       // all of this warp's TMEM reads for the tile are done: hand the accumulator back to the leader's MMA warp
       tcgen05_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar + 8 * acc, 0);
     }
     if (lane == 0) tma_store_wait_all();
+    DIAG_STAMP(6);
   }
 
   tcgen05_before_sync();

@@ -89,6 +89,62 @@ __global__ void __launch_bounds__(96, 1) l1_stream_kernel(const __grid_constant_
   }
 }
 
+
+// Pair mode: the CTA-pair structure of gemm_tf32_2cta_kernel without the MMAs.  Cluster (2,1,1); pair q streams a
+// contiguous range of (256-row tile, K block) units; CTA rank r loads its 128 rows of A (+ its half of the B tile)
+// with cp.async.bulk.tensor...cta_group::2 completing on the LEADER's full barrier; the leader's consumer waits for
+// both CTAs' bytes, optionally spins `consume_cycles`, and frees the slot in both CTAs.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(96, 1) l1_stream_pair_kernel(const __grid_constant__ P p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bars[32];     // full[16] empty[16]
+  const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[16]);
+  const uint32_t crank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 16; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 1); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  const int npairs = gridDim.x / 2, pair = blockIdx.x / 2;
+  const int tiles = p.row_tiles / 2;
+  const long long U = (long long)tiles * p.total_kb;
+  const long long u0 = U * pair / npairs, u1 = U * (pair + 1) / npairs;
+  const uint32_t stage_bytes = p.use_b ? 32768u : 16384u;
+  const uint32_t full_leader = mapa_cluster(full, 0);
+  const int warp = threadIdx.x >> 5;
+  long long t0 = clock64();
+  if (warp == 0 && threadIdx.x == 0) {
+    int s = 0; uint32_t ph = 0;
+    for (long long u = u0; u < u1;) {
+      const int nb = (int)((u1 - u < p.burst) ? (u1 - u) : p.burst);
+      { int s2 = s; uint32_t ph2 = ph;
+        for (int j = 0; j < nb; ++j) { mbar_wait(empty + 8 * s2, ph2 ^ 1u); if (++s2 == p.a_stages) { s2 = 0; ph2 ^= 1u; } } }
+      for (int j = 0; j < nb; ++j, ++u) {
+        const int tile = (int)(u / p.total_kb), kb = (int)(u % p.total_kb);
+        if (crank == 0) mbar_expect_tx(full + 8 * s, 2 * stage_bytes);
+        if (p.wgrad) tma_load_3d_2sm(base + s * stage_bytes, &p.a, full_leader + 8 * s, 0, kb * 32, tile * 8 + crank * 4);
+        else         tma_load_2d_2sm(base + s * stage_bytes, &p.a, full_leader + 8 * s, kb * 32, tile * 256 + crank * 128);
+        if (p.use_b) tma_load_3d_2sm(base + s * stage_bytes + 16384u, &p.b, full_leader + 8 * s, 0, kb * 32, crank * 4);
+        if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 2 && threadIdx.x == 64 && crank == 0) {
+    int s = 0; uint32_t ph = 0;
+    for (long long u = u0; u < u1; ++u) {
+      mbar_wait(full + 8 * s, ph);
+      if (p.consume_cycles) { long long t = clock64(); while (clock64() - t < p.consume_cycles) { } }
+      mbar_arrive(empty + 8 * s);
+      mbar_arrive_cluster(empty + 8 * s, 1);
+      if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+    }
+    p.out[blockIdx.x * 3] = clock64() - t0; p.out[blockIdx.x * 3 + 1] = 0; p.out[blockIdx.x * 3 + 2] = u1 - u0;
+    p.out[(blockIdx.x + 1) * 3] = clock64() - t0;
+  }
+  __syncthreads();
+  cluster_sync_all();
+}
+
 int main(int argc, char** argv) {
   const bool same_buffer = argc > 1;      // any argument: re-read the SAME buffer every launch (like scripts/profile_gemm.py)
   void* fn = nullptr; cudaDriverEntryPointQueryResult q;
@@ -193,6 +249,38 @@ int main(int argc, char** argv) {
       long long mn = 1LL << 60, mx = 0; double avg = 0;
       for (int i = 0; i < 148; ++i) { mn = std::min(mn, h[3 * i]); mx = std::max(mx, h[3 * i]); avg += h[3 * i] / 148.0; }
       printf("%-44s %7.1f us  A %.2f TB/s  | per-CTA cycles min %lld avg %.0f max %lld\n", v.name, best * 1e3, (double)M * LD * 4 / best / 1e9, mn, avg, mx);
+    }
+  }
+  // ---- pair mode (forward pattern and weight-gradient pattern) ----
+  {
+    cudaFuncSetAttribute(l1_stream_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    struct Q { const char* name; int wgrad, use_b, st, consume, burst; };
+    Q qs[] = {{"PAIR fwd A only 12 x 16 KB burst 1", 0, 0, 12, 0, 1}, {"PAIR fwd A only 12 x 16 KB burst 2", 0, 0, 12, 0, 2}, {"PAIR fwd A only 12 x 16 KB burst 3", 0, 0, 12, 0, 3},
+              {"PAIR fwd A+B 6 x 32 KB burst 1, consumer 512", 0, 1, 6, 512, 1}, {"PAIR fwd A+B 6 x 32 KB burst 2, consumer 512", 0, 1, 6, 512, 2}, {"PAIR fwd A+B 6 x 32 KB burst 3, consumer 512", 0, 1, 6, 512, 3},
+              {"PAIR fwd A+B 6 x 32 KB burst 1, consumer 128", 0, 1, 6, 128, 1}, {"PAIR fwd A+B 6 x 32 KB burst 2, consumer 128", 0, 1, 6, 128, 2},
+              {"PAIR wgrad A+B 6 x 32 KB burst 1, consumer 512", 1, 1, 6, 512, 1}, {"PAIR wgrad A+B 6 x 32 KB burst 2, consumer 512", 1, 1, 6, 512, 2}};
+    for (auto& v : qs) {
+      P q; memset(&q, 0, sizeof q);
+      if (v.wgrad) {
+        cuuint64_t dims[3] = {32, (cuuint64_t)M, (cuuint64_t)((K + 31) / 32)}; cuuint64_t str[2] = {(cuuint64_t)LD * 4, 128}; cuuint32_t box[3] = {32, 32, 4}; cuuint32_t es[3] = {1, 1, 1};
+        encode(&q.a, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, A, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        q.total_kb = M / 32; q.row_tiles = 2 * ((K + 255) / 256);
+      } else {
+        q.a = p.a; q.total_kb = (K + 31) / 32; q.row_tiles = M / 128;
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M}; cuuint64_t str[1] = {(cuuint64_t)LD * 4}; cuuint32_t box[2] = {32, 128}; cuuint32_t es[2] = {1, 1};
+        encode(&q.a, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, A, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      q.b = p.b; q.wgrad = v.wgrad; q.use_b = v.use_b; q.a_stages = v.st; q.burst = v.burst; q.consume_cycles = v.consume; q.out = d;
+      float best = 1e9;
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        l1_stream_pair_kernel<<<148, 96, 225 * 1024>>>(q);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep > 0 && ms < best) best = ms;
+      }
+      printf("%-52s %7.1f us  A %.2f TB/s\n", v.name, best * 1e3, (double)M * LD * 4 / best / 1e9);
     }
   }
   return 0;
