@@ -467,6 +467,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
       }
       ++w.side_issued;
     }
+    // stream-K owner: the FIRST contributor's partial of the next chunk is fetched one chunk ahead (under the
+    // activation + staged store of the current one); un / c_pref carry it across iterations
+    float4 un[8];
+    int c_pref = -1;
+    auto sk_slot = [&](int pr, int cc) {
+      return reinterpret_cast<const float4*>(p.sk_ws + (static_cast<size_t>(pr) * 2 + sk_cta) * SK_SLOT_FLOATS) +
+             static_cast<size_t>(cc) * 8 * 128 + (32 * q + lane);
+    };
+    if (sk_mode == 2 && c_first < c_end && cpart < nchunks && nt * p.bn + cpart * 32 < p.N) {
+      const float4* s0 = sk_slot(c_first, cpart);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) un[j] = __ldcg(s0 + j * 128);
+      c_pref = cpart;
+    }
     for (int c = cpart; c < nchunks; c += CPARTS) {
       const int n0 = nt * p.bn + c * 32;
       if (n0 >= p.N) break;
@@ -499,10 +513,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
           // add the other pairs' partial accumulators of this tile, in pair order (deterministic).  Two contributors'
           // loads are in flight together: this fix-up sits on the kernel's critical path (diagnostic builds: the
           // stream-K tail is 16 of the layer-1 products' 76 us) and each load is an L2 round trip.
-          const size_t slot_off = static_cast<size_t>(c) * 8 * 128 + (32 * q + lane);
-          auto slot = [&](int pr) {
-            return reinterpret_cast<const float4*>(p.sk_ws + (static_cast<size_t>(pr) * 2 + sk_cta) * SK_SLOT_FLOATS) + slot_off;
-          };
           auto add8 = [&](const float4 (&u)[8]) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -513,10 +523,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
             }
           };
           int pr = c_first;
+          if (c_pref == c) {                    // first contributor: already in registers
+            if (pr + 1 < c_end) {               // second one in flight while the first is added
+              float4 u1[8];
+              const float4* s1 = sk_slot(pr + 1, c);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) u1[j] = __ldcg(s1 + j * 128);
+              add8(un);
+              add8(u1);
+              pr += 2;
+            } else {
+              add8(un);
+              pr += 1;
+            }
+          }
           for (; pr + 1 < c_end; pr += 2) {
             float4 u0[8], u1[8];
-            const float4* s0 = slot(pr);
-            const float4* s1 = slot(pr + 1);
+            const float4* s0 = sk_slot(pr, c);
+            const float4* s1 = sk_slot(pr + 1, c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) u0[j] = __ldcg(s0 + j * 128);   // written by another SM during this launch: L2 only
 #pragma unroll
@@ -526,10 +550,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiWarp& w, i
           }
           if (pr < c_end) {
             float4 u0[8];
-            const float4* s0 = slot(pr);
+            const float4* s0 = sk_slot(pr, c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) u0[j] = __ldcg(s0 + j * 128);
             add8(u0);
+          }
+          const int cn2 = c + CPARTS;           // next chunk's first contributor: in flight under this chunk's store
+          if (c_first < c_end && cn2 < nchunks && nt * p.bn + cn2 * 32 < p.N) {
+            const float4* s0 = sk_slot(c_first, cn2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) un[j] = __ldcg(s0 + j * 128);
+            c_pref = cn2;
           }
         }
         if (e.act == 1) {
