@@ -2,7 +2,10 @@
 // a contiguous range of (128-row tile, K block) units of A [12288 x 6608] fp32 (HBM stream, 16 KB boxes [128][128 B])
 // and, per K block, 16 KB of the L2-resident B [6605 x 200] (3-D MN-major map, 4 chunks), like one CTA of a pair.
 // Variants: coupled ring (A and B share a stage, as the GEMM does) vs decoupled rings (deep A ring, shallow B ring),
-// B on/off.  Reports aggregate TB/s of A, and the per-CTA cycle spread grouped by SM id (GPC imbalance).
+// B on/off, grouped issue ("burst"), a consumer delay, the weight-gradient pattern, and a CTA-PAIR mode (cluster of 2,
+// cta_group::2 loads completing on the leader's barrier).  Reports aggregate TB/s of A and the per-CTA cycle spread.
+// Any argument: re-read the same buffer every launch (as scripts/profile_gemm.py does) instead of alternating two.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o l1_stream l1_stream.cu -lcuda
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
