@@ -385,8 +385,8 @@ def dominant_kernel_roofline(tr, batch, torch, pk, tf32_peak, n_critic=5, genera
     dom = max(out, key=lambda r: r["ms"] * r["per_step"])
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernel + shape from the committed
     # `ncu --set full` captures (reference dims, batch 4096 only); null for shapes that were not captured
-    NCU_TRAFFIC = {"critic layer-1 forward": (342.23e6 + 11.76e6, "profiles/r02_ncu_full_critic_l1_forward.txt"),
-                   "critic layer-1 weight gradient": (355.40e6 + 8.31e6, "profiles/r02_ncu_full_critic_l1_wgrad.txt"),
+    NCU_TRAFFIC = {"critic layer-1 forward": (342.51e6 + 12.86e6, "profiles/r02_ncu_full_critic_l1_forward.txt"),
+                   "critic layer-1 weight gradient": (355.25e6 + 8.50e6, "profiles/r02_ncu_full_critic_l1_wgrad.txt"),
                    "generator output forward [": (26.54e6 + 55.65e6, "profiles/r02_ncu_full_generator_output.txt"),
                    "generator output forward with the fused interpolate": (168.31e6 + 165.39e6,
                                                                            "profiles/r02_ncu_full_generator_output.txt")}
@@ -618,7 +618,7 @@ def bench_training(args, ctx):
         torch.cuda.synchronize()
 
     # ---------------- the reference's own configuration: batch 32, no penalty, 1 generator + 1 critic update ----------
-    literal = None
+    literal = small = None
     if extras and world == 1:
         tl = WGANTrainer(WGANConfig.reference_literal(), max_batch=32, device=local)
         keep.append(tl)
@@ -631,6 +631,17 @@ def bench_training(args, ctx):
                    "gpu_iters_per_sec": 1000.0 / l_ms, "gpu_ms_per_iter": l_ms,
                    "gpu_launches_per_iter": int(tl.graph_launches_per_replay)}
         tl._graph_keepalive = None
+        # ... and WGAN-GP at the reference's batch size (lambda 10, n_critic 5, batch 32)
+        ts = WGANTrainer(WGANConfig(lambda_gp=10.0, n_critic=5, **dims), max_batch=32, device=local)
+        keep.append(ts)
+        ts.init_params(seed=0)
+        ts._data, ts._data_max_value = tr._data, tr._data_max_value
+        sreplay = ts.capture_iteration(32, seed=0)
+        s_ms = _timed_replays(ctx, sreplay, 200) / 200
+        small = {"what": "WGAN-GP iteration (5 critic+penalty updates + 1 generator update) at the reference's batch 32 [W:11]",
+                 "gpu_iters_per_sec": 1000.0 / s_ms, "gpu_ms_per_iter": s_ms,
+                 "gpu_launches_per_iter": int(ts.graph_launches_per_replay)}
+        ts._graph_keepalive = None
 
     roof = cpu = None
     if rank == 0:
@@ -646,6 +657,8 @@ def bench_training(args, ctx):
             if literal is not None:
                 spsl, msl, coresl, samplel = time_cpu(2, 32, 50, 5, budget_s=30.0, literal=True)
                 literal.update({"cpu_iters_per_sec": spsl, "cpu_ms_per_iter": msl, "cpu_cores": coresl, "cpu_sample": samplel})
+                spss, mss, coress, samples = time_cpu(2, 32, 20, 3, budget_s=30.0)
+                small.update({"cpu_iters_per_sec": spss, "cpu_ms_per_iter": mss, "cpu_cores": coress, "cpu_sample": samples})
     line = {"metric": c["metric"], "value": value, "unit": c["unit"], "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": c["scaling"],
             "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
@@ -665,6 +678,7 @@ def bench_training(args, ctx):
         line["gram_form"] = gram
     if literal is not None:
         line["reference_literal"] = literal
+        line["wgan_gp_batch32"] = small
     return line, keep
 
 
