@@ -879,9 +879,11 @@ int wgan_create(const wgan_config* cfg, wgan_handle** out) {
   h->dp_win = nullptr; h->dp_win_bytes = 0; h->dp_connected = false;
   h->dp_world = cfg->dp_world > 1 ? cfg->dp_world : 1;
   h->dp_rank = cfg->dp_world > 1 ? cfg->dp_rank : 0;
-  // 32 blocks: alone the exchange is faster with one block per SM (critic arena, 2 GPUs: 32 us vs 42 us), but next
-  // to the kernels it overlaps with the small grid wins: 8 GPUs 2799 vs 2745 iters/s (profiles/r02_scaling.txt)
-  h->dp_blocks = 32;
+  // Few fat blocks: 16 x 1024 threads.  Alone the exchange is fastest with one 256-thread block per SM (critic arena, 2
+  // GPUs: 32 us vs 42 us), but next to the kernels it overlaps with the small grid wins, and fatter blocks more so --
+  // measured iters/s on one box each: 8 GPUs 3106 (16 x 1024) vs 3035 (8 x 1024) vs 3042 (32 x 256) vs 2745 (148 x 256);
+  // 2 GPUs 785 (8 x 1024) vs 783 (16 x 512) vs 771 (32 x 256) vs 738 (148 x 128)  (profiles/r02_scaling.txt)
+  h->dp_blocks = 16;
   h->dp_early_trigger = false;
   h->dp_stream = nullptr; h->dp_fork = nullptr; h->dp_join = nullptr;
   h->aux_stream = nullptr; h->aux_fork = nullptr; h->aux_join = nullptr;
@@ -1581,7 +1583,12 @@ static int dp_exchange_range(wgan_handle* h, int net, size_t off, size_t n, cuda
   p.stage_stride = h->dp_stage_stride;
   p.n4 = n / 4;
   p.early_trigger = h->dp_early_trigger ? 1 : 0;
-  KLAUNCH(dp_allreduce_kernel, h->dp_blocks, DP_THREADS, 0, s, p);
+  static const int dp_threads = [] {
+    const char* e = getenv("WGAN_B200_DP_THREADS");
+    const int t = e ? atoi(e) : DP_THREADS;
+    return (t >= 32 && t <= DP_THREADS && t % 32 == 0) ? t : DP_THREADS;
+  }();
+  KLAUNCH(dp_allreduce_kernel, h->dp_blocks, dp_threads, 0, s, p);
   return post_launch(h, "dp_allreduce_kernel");
 }
 

@@ -805,7 +805,7 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __r
 // ---------------------------------------------------------------------------------------------
 constexpr int DP_MAX_WORLD = 16;
 constexpr int DP_MAX_BLOCKS = 148;
-constexpr int DP_THREADS = 256;
+constexpr int DP_THREADS = 1024;        // block size (WGAN_B200_DP_THREADS lowers it for experiments)
 constexpr int DP_FLAG_WORDS = DP_MAX_BLOCKS * (2 * DP_MAX_WORLD + 1);   // arrive1, arrive2 [block][rank]; epoch[block]
 
 struct DpParams {
@@ -875,10 +875,12 @@ __device__ __forceinline__ void dp_block_part(size_t lo, size_t hi, size_t& b0, 
   b1 = b0 + per < hi ? b0 + per : hi;
 }
 
-// Small footprint on purpose (256 threads, <= 40 registers, no dynamic shared memory): a block fits on an SM next to a
-// persistent GEMM CTA (168 registers x 320 threads, ~200 KB of shared memory), so the exchange of update k really
-// runs beside the generator forward of update k + 1 instead of taking SMs away from it.
-__global__ void __launch_bounds__(DP_THREADS, 6)
+// Launched as a few fat blocks (16 x 1024 threads by default, engine.cu): it runs on a second stream beside the
+// generator forward of the next update, and what matters there is how little it disturbs those kernels, not its own
+// speed -- measured, the fewer SMs it touches the better (a 1024-thread block cannot share an SM with a persistent
+// GEMM CTA, so those 16 SMs simply join the GEMM late), whereas one small block on every SM slowed every CTA a little
+// and the whole persistent grid with it.
+__global__ void __launch_bounds__(DP_THREADS, 1)
 dp_allreduce_kernel(const DpParams p) {
   // early_trigger = 0 (several ranks on one GPU: tests): no griddepcontrol.launch_dependents before the end --
   // blocks of the next kernel parked on the SMs could keep a PEER's blocks (same GPU, other stream) from becoming
@@ -892,6 +894,7 @@ dp_allreduce_kernel(const DpParams p) {
   __syncthreads();
   const unsigned int epoch = s_epoch;
   const int W = p.world, R = p.rank;
+  const size_t nthr = blockDim.x;            // <= DP_THREADS (engine: WGAN_B200_DP_THREADS)
   float4* mine = reinterpret_cast<float4*>(p.peer[R] + p.grad_off);
   // 1. scatter: my contribution to every foreign slice -> its owner's staging row R
   for (int dk = 1; dk < W; ++dk) {
@@ -901,9 +904,9 @@ dp_allreduce_kernel(const DpParams p) {
     dp_block_part(lo, hi, b0, b1);
     float4* dst = reinterpret_cast<float4*>(p.peer[k] + p.stage_off + static_cast<size_t>(R) * p.stage_stride) - lo;
     size_t i = b0 + threadIdx.x;
-    for (; i + DP_THREADS < b1; i += 2 * DP_THREADS) {
-      const float4 v0 = mine[i], v1 = mine[i + DP_THREADS];
-      dp_store_v4(dst + i, v0); dp_store_v4(dst + i + DP_THREADS, v1);
+    for (; i + nthr < b1; i += 2 * nthr) {
+      const float4 v0 = mine[i], v1 = mine[i + nthr];
+      dp_store_v4(dst + i, v0); dp_store_v4(dst + i + nthr, v1);
     }
     if (i < b1) dp_store_v4(dst + i, mine[i]);
   }
@@ -915,7 +918,7 @@ dp_allreduce_kernel(const DpParams p) {
     dp_block_part(lo, hi, b0, b1);
     const float4* stage = reinterpret_cast<const float4*>(p.peer[R] + p.stage_off) - lo;
     const size_t row4 = p.stage_stride / 4;
-    for (size_t i = b0 + threadIdx.x; i < b1; i += DP_THREADS) {
+    for (size_t i = b0 + threadIdx.x; i < b1; i += nthr) {
       float4 acc = (R == 0) ? mine[i] : dp_load_v4(stage + i);
       for (int k = 1; k < W; ++k) {
         const float4 v = (k == R) ? mine[i] : dp_load_v4(stage + static_cast<size_t>(k) * row4 + i);
