@@ -71,3 +71,37 @@ def test_config_defaults_follow_reference():
     o = Adam_Prediction_Optimizer()
     assert (o.learning_rate, o.beta1, o.beta2, o.epsilon, o.prediction, o.use_locking, o.name) == \
            (0.001, 0.9, 0.999, 1e-8, False, False, "Adam")
+
+
+def test_integration_stub_matches_the_header():
+    """INTEGRATION.md's ctypes stub declares struct wgan_config field by field and calls the step entry points with
+    positional arguments: keep both in step with include/wgan_b200.h (they went stale once)."""
+    import re
+    from arshamg_scrnaseq_wgan_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class Cfg(C.Structure)"):text.index("# module constants of the script")]
+    names = re.findall(r'"(\w+)"', block)
+    assert names == [n for n, _ in _lib.WganConfig._fields_], names
+    stub = text[text.index("```python"):text.index("```", text.index("```python") + 10)]
+    for fn in ("wgan_generator_grads", "wgan_critic_grads", "wgan_sample", "wgan_get_scalars"):
+        i = stub.index("lib." + fn + "(")
+        depth, j = 0, i + len("lib." + fn)
+        args, cur = [], ""
+        while True:                                    # split the call's top-level arguments
+            ch = stub[j]
+            if ch == "(":
+                depth += 1
+                if depth > 1:
+                    cur += ch
+            elif ch == ")":
+                depth -= 1
+                if depth == 0:
+                    args.append(cur)
+                    break
+                cur += ch
+            elif ch == "," and depth == 1:
+                args.append(cur); cur = ""
+            else:
+                cur += ch
+            j += 1
+        assert len(args) == len(_lib.SIGNATURES[fn][1]), (fn, args)
