@@ -616,7 +616,9 @@ class WGANTrainer:
                 else:
                     replay()
             if checkpoint_path is not None and (i % save_every == 0 or i == start_step + n - 1):
-                save_checkpoint(self, checkpoint_path, global_step=i + 1)
+                # intermediate dumps carry the step in their name like the reference's Saver [W:203] (none of them
+                # overwrites another); the dump after the last iteration goes to checkpoint_path itself [W:205]
+                save_checkpoint(self, checkpoint_path, global_step=i + 1, step_suffix=i != start_step + n - 1)
         return last
 
     def generate(self, num_cells: Optional[int] = None, seed: int = 0) -> torch.Tensor:
