@@ -108,7 +108,7 @@ class WGANTrainer:
     ``dp_rank`` / ``dp_world`` are given and ``dp_connect`` is called by hand): every rank passes its batch shard,
     gradients are SUM-all-reduced -- one exchange per optimizer step over the flat gradient arena, done by the
     library's own kernel over NVLink peer memory (``wgan_allreduce_grads``) -- and Adam runs replicated.
-    ``torch.distributed`` only carries the 128-byte rendezvous blobs.  ``dp_backend="nccl"`` keeps the
+    ``torch.distributed`` only carries the 192-byte rendezvous blobs.  ``dp_backend="nccl"`` keeps the
     round-1 ``torch.distributed.all_reduce`` exchange for A/B measurements."""
 
     def __init__(self, cfg: WGANConfig, max_batch: Optional[int] = None, device: Optional[int] = None,
